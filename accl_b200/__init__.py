@@ -1,0 +1,34 @@
+"""accl_b200 — ACCL-compatible collectives for NVIDIA B200 (NVLink 5 / NVSwitch).
+
+Backends: `cuda` (symmetric NVLink heap, hand-written sm_100a kernels, a
+persistent engine kernel, NVLS multicast) and `emulator` (CPU model of the
+engine; runs the whole host API and test matrix without a GPU).
+"""
+import importlib
+import os
+import sys
+
+
+def _load_native():
+    try:
+        return importlib.import_module("accl_b200._C")
+    except ImportError as first:
+        # build in-tree on first use (needs g++; nvcc for the CUDA backend)
+        from .utils import build as _b
+        have_nvcc = os.path.exists(_b.NVCC)
+        try:
+            _b.build(with_cuda=have_nvcc)
+        except Exception as e:  # noqa: BLE001
+            raise ImportError(f"accl_b200 native core is not built and building failed: {e}") from first
+        return importlib.import_module("accl_b200._C")
+
+
+_C = _load_native()
+sys.modules.setdefault("accl_b200._C", _C)
+
+from .core import (Accl, Buffer, BufferKind, DataType, GLOBAL_COMM, MAX, ReduceFunction, SUM, TAG_ANY,  # noqa: E402
+                   emulator_world, run_ranks, socket_rank)
+
+__all__ = ["Accl", "Buffer", "BufferKind", "DataType", "GLOBAL_COMM", "MAX", "ReduceFunction", "SUM", "TAG_ANY",
+           "emulator_world", "run_ranks", "socket_rank", "_C"]
+__version__ = "0.1.0"

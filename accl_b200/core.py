@@ -1,0 +1,368 @@
+"""Python face of the library: `Accl` (one per rank) and `Buffer`.
+
+Thin by design — every call lands in the C++ facade `accl::ACCL`
+(csrc/include/accl/accl.hpp), which mirrors the reference API
+(driver/xrt/include/accl.hpp).  What Python adds: torch/numpy views of buffer
+memory, dtype mapping, stream plumbing (the current torch CUDA stream is
+forwarded to the backend) and world construction helpers.
+"""
+import os
+import threading
+
+import numpy as np
+import torch
+
+from . import _C
+from .utils.dtypes import to_accl, to_torch
+
+DataType = _C.DataType
+ReduceFunction = _C.ReduceFunction
+BufferKind = _C.BufferKind
+TAG_ANY = _C.TAG_ANY
+GLOBAL_COMM = _C.GLOBAL_COMM
+SUM = _C.ReduceFunction.SUM
+MAX = _C.ReduceFunction.MAX
+
+
+class _CudaView:
+    """Minimal __cuda_array_interface__ carrier so torch can alias heap memory."""
+
+    def __init__(self, ptr, nbytes, owner):
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None,
+        }
+        self._owner = owner
+
+
+class Buffer:
+    """A library buffer: `.host` is a torch tensor aliasing the host side,
+    `.dev` (CUDA backend) a torch tensor aliasing the device side inside the
+    symmetric NVLink heap (zero-copy operand for every collective)."""
+
+    def __init__(self, impl, accl):
+        self._b = impl
+        self._accl = accl
+        self._host = None
+        self._dev = None
+
+    @property
+    def impl(self):
+        return self._b
+
+    @property
+    def dtype(self):
+        return self._b.dtype
+
+    @property
+    def length(self):
+        return self._b.length
+
+    @property
+    def nbytes(self):
+        return self._b.size
+
+    @property
+    def address(self):
+        return self._b.address
+
+    @property
+    def host(self):
+        if self._host is None:
+            self._host = torch.frombuffer(self._b.host_view(), dtype=torch.uint8).view(to_torch(self._b.dtype))
+        return self._host
+
+    @property
+    def numpy(self):
+        return self.host.numpy() if self.host.dtype in (torch.float16, torch.float32, torch.float64, torch.int32,
+                                                         torch.int64, torch.int8) else self.host.view(torch.uint8).numpy()
+
+    @property
+    def dev(self):
+        if self._dev is None:
+            ptr = self._b.device_ptr
+            if not ptr:
+                raise RuntimeError("buffer has no CUDA device pointer (emulator backend?)")
+            idx = self._accl.cuda_device
+            view = _CudaView(ptr, self._b.size, self)
+            t = torch.as_tensor(view, device=torch.device("cuda", idx))
+            self._dev = t.view(to_torch(self._b.dtype))
+        return self._dev
+
+    def sync_to_device(self):
+        self._b.sync_to_device()
+
+    def sync_from_device(self):
+        self._b.sync_from_device()
+
+    def slice(self, start, end):
+        return Buffer(self._b.slice(start, end), self._accl)
+
+    def __len__(self):
+        return self._b.length
+
+
+def _impl(buf):
+    return buf._b if isinstance(buf, Buffer) else buf
+
+
+class Accl:
+    """One rank's handle.  Method names and argument order follow accl::ACCL."""
+
+    def __init__(self, impl, rank, world, cuda_device=None):
+        self._a = impl
+        self.rank = rank
+        self.world = world
+        self.cuda_device = cuda_device
+        self.initialized = False
+
+    # ---- setup -----------------------------------------------------------
+    @staticmethod
+    def generate_ranks(world, base_port=5500, max_segment_size=1024, ips=None):
+        """Synthetic rank table (reference: accl_network_utils::generate_ranks)."""
+        return [_C.Rank(ips[i] if ips else "127.0.0.1", base_port + i, i, max_segment_size) for i in range(world)]
+
+    def initialize(self, ranks=None, local_rank=None, n_egr_rx_bufs=16, egr_rx_buf_size=1024, max_egr_size=1024,
+                   max_rndzv_size=32 * 1024):
+        if ranks is None:
+            ranks = self.generate_ranks(self.world, max_segment_size=egr_rx_buf_size)
+        self._a.initialize(ranks, self.rank if local_rank is None else local_rank, n_egr_rx_bufs, egr_rx_buf_size,
+                           max_egr_size, max_rndzv_size)
+        self.initialized = True
+        return self
+
+    def deinit(self):
+        self._a.deinit()
+        self.initialized = False
+
+    @property
+    def impl(self):
+        return self._a
+
+    @property
+    def is_cuda(self):
+        return self._a.device_type() == _C.DeviceType.cuda
+
+    def describe(self):
+        return self._a.describe()
+
+    # ---- buffers ---------------------------------------------------------
+    def create_buffer(self, length, dtype=DataType.float32, kind=BufferKind.device):
+        return Buffer(self._a.create_buffer(int(length), to_accl(dtype), kind), self)
+
+    def create_buffer_host(self, length, dtype=DataType.float32):
+        return self.create_buffer(length, dtype, BufferKind.host_only)
+
+    def create_buffer_p2p(self, length, dtype=DataType.float32):
+        return self.create_buffer(length, dtype, BufferKind.p2p)
+
+    def wrap(self, array):
+        """Wrap caller-owned host memory (numpy array or CPU torch tensor)."""
+        if isinstance(array, torch.Tensor):
+            assert array.device.type == "cpu" and array.is_contiguous()
+            b = self._a.wrap_buffer(array.data_ptr(), array.numel(), to_accl(array.dtype))
+        else:
+            array = np.ascontiguousarray(array)
+            b = self._a.wrap_buffer(array.ctypes.data, array.size, to_accl(array.dtype))
+        buf = Buffer(b, self)
+        buf._keep = array
+        return buf
+
+    # ---- call helpers ----------------------------------------------------
+    def _stream(self):
+        if self.is_cuda and self.cuda_device is not None:
+            self._a.set_stream(torch.cuda.current_stream(self.cuda_device).cuda_stream)
+
+    def _cd(self, compress_dtype):
+        return DataType.none if compress_dtype is None else to_accl(compress_dtype)
+
+    # ---- primitives ------------------------------------------------------
+    def nop(self, run_async=False):
+        self._stream()
+        return self._a.nop(run_async)
+
+    def send(self, srcbuf, count, dst, tag=TAG_ANY, comm_id=GLOBAL_COMM, from_fpga=False, compress_dtype=None,
+             run_async=False):
+        self._stream()
+        return self._a.send(_impl(srcbuf), count, dst, tag, comm_id, from_fpga, self._cd(compress_dtype), run_async)
+
+    def send_from_stream(self, dtype, count, dst, tag=TAG_ANY, comm_id=GLOBAL_COMM, compress_dtype=None,
+                         run_async=False):
+        return self._a.send_from_stream(to_accl(dtype), count, dst, tag, comm_id, self._cd(compress_dtype), run_async)
+
+    def stream_put(self, srcbuf, count, dst, stream_id, comm_id=GLOBAL_COMM, from_fpga=False, compress_dtype=None,
+                   run_async=False):
+        self._stream()
+        return self._a.stream_put(_impl(srcbuf), count, dst, stream_id, comm_id, from_fpga, self._cd(compress_dtype),
+                                  run_async)
+
+    def recv(self, dstbuf, count, src, tag=TAG_ANY, comm_id=GLOBAL_COMM, to_fpga=False, compress_dtype=None,
+             run_async=False):
+        self._stream()
+        return self._a.recv(_impl(dstbuf), count, src, tag, comm_id, to_fpga, self._cd(compress_dtype), run_async)
+
+    def recv_to_stream(self, dtype, count, src, tag=TAG_ANY, comm_id=GLOBAL_COMM, compress_dtype=None,
+                       run_async=False):
+        return self._a.recv_to_stream(to_accl(dtype), count, src, tag, comm_id, self._cd(compress_dtype), run_async)
+
+    def copy(self, srcbuf, dstbuf, count, from_fpga=False, to_fpga=False, run_async=False):
+        self._stream()
+        return self._a.copy(_impl(srcbuf), _impl(dstbuf), count, from_fpga, to_fpga, run_async)
+
+    def copy_from_stream(self, dstbuf, count, to_fpga=False, run_async=False):
+        return self._a.copy_from_stream(_impl(dstbuf), count, to_fpga, run_async)
+
+    def copy_to_stream(self, srcbuf, count, from_fpga=False, run_async=False):
+        return self._a.copy_to_stream(_impl(srcbuf), count, from_fpga, run_async)
+
+    def copy_from_to_stream(self, dtype, count, run_async=False):
+        return self._a.copy_from_to_stream(to_accl(dtype), count, run_async)
+
+    def combine(self, count, function, val1, val2, result, val1_from_fpga=False, val2_from_fpga=False, to_fpga=False,
+                run_async=False):
+        self._stream()
+        return self._a.combine(count, function, _impl(val1), _impl(val2), _impl(result), val1_from_fpga,
+                               val2_from_fpga, to_fpga, run_async)
+
+    # ---- collectives -----------------------------------------------------
+    def bcast(self, buf, count, root, comm_id=GLOBAL_COMM, from_fpga=False, to_fpga=False, compress_dtype=None,
+              run_async=False):
+        self._stream()
+        return self._a.bcast(_impl(buf), count, root, comm_id, from_fpga, to_fpga, self._cd(compress_dtype), run_async)
+
+    def scatter(self, sendbuf, recvbuf, count, root, comm_id=GLOBAL_COMM, from_fpga=False, to_fpga=False,
+                compress_dtype=None, run_async=False):
+        self._stream()
+        return self._a.scatter(_impl(sendbuf), _impl(recvbuf), count, root, comm_id, from_fpga, to_fpga,
+                               self._cd(compress_dtype), run_async)
+
+    def gather(self, sendbuf, recvbuf, count, root, comm_id=GLOBAL_COMM, from_fpga=False, to_fpga=False,
+               compress_dtype=None, run_async=False):
+        self._stream()
+        return self._a.gather(_impl(sendbuf), _impl(recvbuf), count, root, comm_id, from_fpga, to_fpga,
+                              self._cd(compress_dtype), run_async)
+
+    def allgather(self, sendbuf, recvbuf, count, comm_id=GLOBAL_COMM, from_fpga=False, to_fpga=False,
+                  compress_dtype=None, run_async=False):
+        self._stream()
+        return self._a.allgather(_impl(sendbuf), _impl(recvbuf), count, comm_id, from_fpga, to_fpga,
+                                 self._cd(compress_dtype), run_async)
+
+    def reduce(self, sendbuf, recvbuf, count, root, func=SUM, comm_id=GLOBAL_COMM, from_fpga=False, to_fpga=False,
+               compress_dtype=None, run_async=False):
+        self._stream()
+        return self._a.reduce(_impl(sendbuf), _impl(recvbuf), count, root, func, comm_id, from_fpga, to_fpga,
+                              self._cd(compress_dtype), run_async)
+
+    def reduce_stream2mem(self, src_dtype, recvbuf, count, root, func=SUM, comm_id=GLOBAL_COMM, to_fpga=False,
+                          compress_dtype=None, run_async=False):
+        return self._a.reduce_stream2mem(to_accl(src_dtype), _impl(recvbuf), count, root, func, comm_id, to_fpga,
+                                         self._cd(compress_dtype), run_async)
+
+    def reduce_mem2stream(self, sendbuf, dst_dtype, count, root, func=SUM, comm_id=GLOBAL_COMM, from_fpga=False,
+                          compress_dtype=None, run_async=False):
+        return self._a.reduce_mem2stream(_impl(sendbuf), to_accl(dst_dtype), count, root, func, comm_id, from_fpga,
+                                         self._cd(compress_dtype), run_async)
+
+    def reduce_stream2stream(self, src_dtype, dst_dtype, count, root, func=SUM, comm_id=GLOBAL_COMM,
+                             compress_dtype=None, run_async=False):
+        return self._a.reduce_stream2stream(to_accl(src_dtype), to_accl(dst_dtype), count, root, func, comm_id,
+                                            self._cd(compress_dtype), run_async)
+
+    def allreduce(self, sendbuf, recvbuf, count, func=SUM, comm_id=GLOBAL_COMM, from_fpga=False, to_fpga=False,
+                  compress_dtype=None, run_async=False):
+        self._stream()
+        return self._a.allreduce(_impl(sendbuf), _impl(recvbuf), count, func, comm_id, from_fpga, to_fpga,
+                                 self._cd(compress_dtype), run_async)
+
+    def reduce_scatter(self, sendbuf, recvbuf, count, func=SUM, comm_id=GLOBAL_COMM, from_fpga=False, to_fpga=False,
+                       compress_dtype=None, run_async=False):
+        self._stream()
+        return self._a.reduce_scatter(_impl(sendbuf), _impl(recvbuf), count, func, comm_id, from_fpga, to_fpga,
+                                      self._cd(compress_dtype), run_async)
+
+    def alltoall(self, sendbuf, recvbuf, count, comm_id=GLOBAL_COMM, from_fpga=False, to_fpga=False,
+                 compress_dtype=None, run_async=False):
+        self._stream()
+        return self._a.alltoall(_impl(sendbuf), _impl(recvbuf), count, comm_id, from_fpga, to_fpga,
+                                self._cd(compress_dtype), run_async)
+
+    def barrier(self, comm_id=GLOBAL_COMM):
+        self._stream()
+        return self._a.barrier(comm_id)
+
+    # ---- communicators / config / introspection --------------------------
+    def create_communicator(self, ranks, local_rank):
+        return self._a.create_communicator(ranks, local_rank)
+
+    def get_comm_group(self, comm_id=GLOBAL_COMM):
+        return self._a.get_comm_group(comm_id)
+
+    def get_comm_rank(self, comm_id=GLOBAL_COMM):
+        return self._a.get_comm_rank(comm_id)
+
+    def set_timeout(self, value):
+        self._a.set_timeout(value)
+
+    def set_max_eager_msg_size(self, value):
+        self._a.set_max_eager_msg_size(value)
+
+    def set_max_rendezvous_msg_size(self, value):
+        self._a.set_max_rendezvous_msg_size(value)
+
+    def dump_communicator(self):
+        return self._a.dump_communicator()
+
+    def dump_exchange_memory(self):
+        return self._a.dump_exchange_memory()
+
+    def dump_eager_rx_buffers(self, dump_data=False):
+        return self._a.dump_eager_rx_buffers(dump_data)
+
+    def __getattr__(self, name):  # anything not wrapped above goes straight to C++
+        return getattr(self._a, name)
+
+
+def emulator_world(world_size, mem_mb=256):
+    """N un-initialised ranks of an in-process CPU emulator (drive each from its own thread)."""
+    return [Accl(a, r, world_size) for r, a in enumerate(_C.make_emu_world(world_size, mem_mb))]
+
+
+def run_ranks(world_size, fn, init_kwargs=None, mem_mb=64, timeout=120.0):
+    """Run fn(accl, rank, world) on every rank of a fresh emulator world, one
+    thread per rank; re-raises the first failure.  The harness used by the CPU
+    test-suite (the reference uses mpirun + one emulator process per rank)."""
+    accls = emulator_world(world_size, mem_mb)
+    errors = [None] * world_size
+    results = [None] * world_size
+
+    def body(r):
+        try:
+            accls[r].initialize(**(init_kwargs or {}))
+            results[r] = fn(accls[r], r, world_size)
+        except BaseException as e:  # noqa: BLE001 - reported to the caller
+            import traceback
+            errors[r] = (e, traceback.format_exc())
+
+    threads = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(world_size)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout)
+    hung = [r for r, t in enumerate(threads) if t.is_alive()]
+    for r, e in enumerate(errors):
+        if e is not None:
+            raise RuntimeError(f"rank {r} failed:\n{e[1]}") from e[0]
+    if hung:
+        raise TimeoutError(f"ranks {hung} did not finish within {timeout}s")
+    for a in accls:
+        a.deinit()
+    return results
+
+
+def socket_rank(rank=None, world_size=None, addr="127.0.0.1", base_port=None, mem_mb=256):
+    """One emulator rank per process (torchrun / mpirun style), loopback TCP between ranks."""
+    rank = int(os.environ.get("RANK", 0)) if rank is None else rank
+    world_size = int(os.environ.get("WORLD_SIZE", 1)) if world_size is None else world_size
+    if base_port is None:
+        base_port = int(os.environ.get("ACCL_EMU_PORT", int(os.environ.get("MASTER_PORT", 29500)) + 100))
+    return Accl(_C.make_emu_socket(rank, world_size, addr, base_port, mem_mb), rank, world_size)

@@ -1,0 +1,129 @@
+"""In-tree build of the native core (C++17 host code + sm_100a CUDA).
+
+`python -m accl_b200.utils.build` compiles every source under csrc/ and links
+`accl_b200/_C*.so` (pybind11 module, static cudart, no libcuda link: the driver
+API is resolved lazily so the module imports on GPU-less machines) plus the
+standalone tools under build/bin.  nvcc cross-compiles for sm_100a without a
+GPU; the resulting .so travels to the GPU box as-is.
+
+Replaces the reference's CMake/Make/Vitis flow (driver/xrt/CMakeLists.txt,
+kernels/cclo/Makefile, test/refdesigns/Makefile).
+"""
+import concurrent.futures as cf
+import os
+import shlex
+import subprocess
+import sys
+import sysconfig
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[2]
+CSRC = ROOT / "csrc"
+OBJ = ROOT / "build" / "obj"
+BIN = ROOT / "build" / "bin"
+
+NVCC = os.environ.get("ACCL_NVCC", "/usr/local/cuda/bin/nvcc")
+CXX = os.environ.get("ACCL_CXX", "/usr/bin/g++")  # NOT $CXX: the image exports a toolchain whose libstdc++ is static
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+HOST_SOURCES = [
+    "src/host/accl.cpp", "src/host/arithconfig.cpp", "src/host/bootstrap.cpp", "src/host/common.cpp",
+    "src/host/communicator.cpp", "src/host/constants.cpp",
+    "src/emu/engine.cpp", "src/emu/firmware.cpp", "src/emu/fabric.cpp", "src/emu/emudevice.cpp",
+]
+CUDA_HOST_SOURCES = ["src/cuda/driver_api.cpp", "src/cuda/symheap.cpp"]
+CUDA_SOURCES = []  # filled below from csrc/src/cuda/*.cu
+BINDING = "bindings/pyaccl.cpp"
+
+
+def _includes():
+    import pybind11
+    return ["-I" + str(CSRC / "include"), "-I" + pybind11.get_include(),
+            "-I" + sysconfig.get_paths()["include"], "-I/usr/local/cuda/include"]
+
+
+def _newest_header_mtime():
+    m = 0.0
+    for p in (CSRC / "include").rglob("*"):
+        if p.is_file():
+            m = max(m, p.stat().st_mtime)
+    for p in (CSRC / "src").rglob("*.hpp"):
+        m = max(m, p.stat().st_mtime)
+    for p in (CSRC / "src").rglob("*.cuh"):
+        m = max(m, p.stat().st_mtime)
+    return m
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(shlex.quote(c) for c in cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("build step failed: " + " ".join(cmd[:6]) + " ...")
+    if verbose and (r.stdout or r.stderr):
+        sys.stderr.write(r.stdout + r.stderr)
+
+
+def _compile(src, with_cuda, hdr_mtime, verbose, force):
+    srcp = CSRC / src
+    obj = OBJ / (src.replace("/", "_") + ".o")
+    if not force and obj.exists() and obj.stat().st_mtime > max(srcp.stat().st_mtime, hdr_mtime):
+        return obj
+    defs = ["-DACCL_WITH_CUDA"] if with_cuda else []
+    if src.endswith(".cu"):
+        cmd = [NVCC, "-ccbin", CXX, "-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-fvisibility=hidden",
+               "--expt-relaxed-constexpr", "-Xptxas", "-v" if verbose else "-O3",
+               *defs, *_includes(), "-c", str(srcp), "-o", str(obj)]
+    else:
+        cmd = [CXX, "-std=c++17", "-O2", "-g1", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wno-unused-function",
+               *defs, *_includes(), "-c", str(srcp), "-o", str(obj)]
+    _run(cmd, verbose)
+    return obj
+
+
+def ext_path():
+    return ROOT / "accl_b200" / ("_C" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build(with_cuda=True, verbose=False, force=False, tools=True):
+    OBJ.mkdir(parents=True, exist_ok=True)
+    BIN.mkdir(parents=True, exist_ok=True)
+    cu = sorted(str(p.relative_to(CSRC)) for p in (CSRC / "src" / "cuda").glob("*.cu"))
+    cuda_host = sorted(str(p.relative_to(CSRC)) for p in (CSRC / "src" / "cuda").glob("*.cpp"))
+    srcs = list(HOST_SOURCES) + [BINDING]
+    if with_cuda:
+        srcs += cuda_host + cu
+    hdr = _newest_header_mtime()
+    with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(lambda s: _compile(s, with_cuda, hdr, verbose, force), srcs))
+    out = ext_path()
+    if force or not out.exists() or any(o.stat().st_mtime > out.stat().st_mtime for o in objs):
+        if with_cuda:
+            link = [NVCC, "-ccbin", CXX, "-shared", *ARCH, "-cudart", "static", "-Xcompiler", "-fPIC",
+                    *[str(o) for o in objs], "-o", str(out), "-lpthread", "-ldl", "-lrt"]
+        else:
+            link = [CXX, "-shared", "-fPIC", *[str(o) for o in objs], "-o", str(out), "-lpthread"]
+        _run(link, verbose)
+    if tools and with_cuda:
+        lib_objs = [o for o, s in zip(objs, srcs) if s != BINDING]
+        for tool in sorted((CSRC / "tools").glob("*.cu")) + sorted((CSRC / "tools").glob("*.cpp")):
+            exe = BIN / tool.stem
+            if not force and exe.exists() and exe.stat().st_mtime > max(tool.stat().st_mtime, hdr,
+                                                                        max(o.stat().st_mtime for o in lib_objs)):
+                continue
+            _run([NVCC, "-ccbin", CXX, "-std=c++17", "-O3", "-lineinfo", *ARCH, "--expt-relaxed-constexpr", "-DACCL_WITH_CUDA",
+                  "-I" + str(CSRC / "include"), str(tool), *[str(o) for o in lib_objs], "-o", str(exe),
+                  "-lpthread", "-ldl", "-lrt"], verbose)
+    return out
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cpu-only", action="store_true")
+    ap.add_argument("-v", "--verbose", action="store_true")
+    ap.add_argument("-f", "--force", action="store_true")
+    ap.add_argument("--no-tools", action="store_true")
+    a = ap.parse_args()
+    print(build(with_cuda=not a.cpu_only, verbose=a.verbose, force=a.force, tools=not a.no_tools))
