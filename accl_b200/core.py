@@ -170,7 +170,10 @@ class Accl:
     # ---- call helpers ----------------------------------------------------
     def _stream(self):
         if self.is_cuda and self.cuda_device is not None:
-            self._a.set_stream(torch.cuda.current_stream(self.cuda_device).cuda_stream)
+            h = torch.cuda.current_stream(self.cuda_device).cuda_stream
+            # 0 is torch's legacy default stream: name it explicitly (cudaStreamLegacy)
+            # so calls stay ordered with tensor ops issued on it
+            self._a.set_stream(h if h else 1)
 
     def _cd(self, compress_dtype):
         return DataType.none if compress_dtype is None else to_accl(compress_dtype)
@@ -366,3 +369,71 @@ def socket_rank(rank=None, world_size=None, addr="127.0.0.1", base_port=None, me
     if base_port is None:
         base_port = int(os.environ.get("ACCL_EMU_PORT", int(os.environ.get("MASTER_PORT", 29500)) + 100))
     return Accl(_C.make_emu_socket(rank, world_size, addr, base_port, mem_mb), rank, world_size)
+
+
+# --------------------------------------------------------------------- CUDA
+def _prepare_cuda_env():
+    # ranks sharing one process/GPU need independent hardware queues, or one
+    # rank's spinning kernel can block the launch of the peer it waits for
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
+def cuda_world(devices, heap_mb=256, multicast=True, max_ctas=8, engine=False, nvls_min_ranks=3, oneshot_kb=512):
+    """In-process world on real GPUs: rank i drives devices[i] (a device may
+    appear several times: ranks then share that GPU, without NVLS)."""
+    _prepare_cuda_env()
+    impls = _C.make_cuda_world(list(devices), heap_mb, multicast, max_ctas, engine, nvls_min_ranks, oneshot_kb)
+    return [Accl(a, r, len(devices), cuda_device=devices[r]) for r, a in enumerate(impls)]
+
+
+def cuda_rank(rank=None, world_size=None, device=None, addr=None, port=None, heap_mb=1024, multicast=True,
+              max_ctas=32, engine=False, nvls_min_ranks=3, oneshot_kb=512):
+    """One rank per process (torchrun): RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT."""
+    _prepare_cuda_env()
+    rank = int(os.environ.get("RANK", 0)) if rank is None else rank
+    world_size = int(os.environ.get("WORLD_SIZE", 1)) if world_size is None else world_size
+    device = int(os.environ.get("LOCAL_RANK", rank)) if device is None else device
+    addr = os.environ.get("MASTER_ADDR", "127.0.0.1") if addr is None else addr
+    if addr == "localhost":
+        addr = "127.0.0.1"
+    if port is None:
+        port = int(os.environ.get("ACCL_PORT", int(os.environ.get("MASTER_PORT", 29500)) + 137))
+    impl = _C.make_cuda_rank(rank, world_size, device, addr, port, heap_mb, multicast, max_ctas, engine,
+                             nvls_min_ranks, oneshot_kb)
+    return Accl(impl, rank, world_size, cuda_device=device)
+
+
+def run_cuda_ranks(devices, fn, init_kwargs=None, timeout=180.0, **cfg):
+    """Threads-as-ranks harness on GPUs (the CUDA twin of run_ranks)."""
+    accls = cuda_world(devices, **cfg)
+    world = len(devices)
+    errors = [None] * world
+    results = [None] * world
+
+    def body(r):
+        try:
+            torch.cuda.set_device(devices[r])
+            # one torch stream per rank: ranks sharing a GPU must never queue on the same stream
+            with torch.cuda.stream(torch.cuda.Stream(devices[r])):
+                accls[r].initialize(**(init_kwargs or {}))
+                results[r] = fn(accls[r], r, world)
+                torch.cuda.current_stream().synchronize()
+        except BaseException as e:  # noqa: BLE001
+            import traceback
+            errors[r] = (e, traceback.format_exc())
+
+    threads = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout)
+    hung = [r for r, t in enumerate(threads) if t.is_alive()]
+    for r, e in enumerate(errors):
+        if e is not None:
+            raise RuntimeError(f"rank {r} failed:\n{e[1]}") from e[0]
+    if hung:
+        raise TimeoutError(f"ranks {hung} did not finish within {timeout}s")
+    for a in accls:
+        a.deinit()
+    del accls
+    return results

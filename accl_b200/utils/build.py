@@ -106,7 +106,7 @@ def build(with_cuda=True, verbose=False, force=False, tools=True):
             link = [CXX, "-shared", "-fPIC", *[str(o) for o in objs], "-o", str(out), "-lpthread"]
         _run(link, verbose)
     if tools and with_cuda:
-        lib_objs = [o for o, s in zip(objs, srcs) if s != BINDING]
+        lib_objs = [o for o, s in zip(objs, srcs) if s != BINDING and "bind_" not in s]
         for tool in sorted((CSRC / "tools").glob("*.cu")) + sorted((CSRC / "tools").glob("*.cpp")):
             exe = BIN / tool.stem
             if not force and exe.exists() and exe.stat().st_mtime > max(tool.stat().st_mtime, hdr,

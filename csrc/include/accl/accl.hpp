@@ -174,7 +174,10 @@ public:
   addr_t max_eager_size() const { return max_eager_size_; }
   addr_t max_rendezvous_size() const { return max_rndzv_size_; }
   // GPU: enqueue subsequent calls on this cudaStream_t (nullptr = backend stream)
-  void set_stream(void *stream) { stream_ = stream; }
+  void set_stream(void *stream) {
+    stream_ = stream;
+    cclo->set_stream(stream);
+  }
   void *get_stream() const { return stream_; }
 
   // no-ops kept for source compatibility (TCP session management in the reference)

@@ -100,6 +100,8 @@ public:
   virtual deviceType get_device_type() = 0;
   virtual std::string describe() = 0;
   virtual void printDebug() {}
+  // GPU backends: stream on which subsequent calls and buffer syncs are enqueued
+  virtual void set_stream(void *stream) { (void)stream; }
 
   // backend-owned memory
   virtual std::shared_ptr<BufferStorage> allocate(size_t bytes, bufferKind kind) = 0;

@@ -1,0 +1,133 @@
+// CudaDevice: the B200 backend.  Owns the symmetric NVLink heap (control
+// block + eager slots + user buffers), selects protocol/algorithm per call,
+// and executes calls either by direct stream-ordered kernel launch or through
+// the persistent engine kernel (command rings in device memory).
+//
+// Reference counterparts: XRTDevice / CoyoteDevice (driver/xrt/src/xrtdevice.cpp,
+// coyotedevice.cpp) for the call path, XRTBuffer for storage, and the
+// firmware's per-call decisions (ccl_offload_control.c:2308-2483) for
+// `plan()`.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "accl/allocator.hpp"
+#include "accl/bootstrap.hpp"
+#include "accl/cclo.hpp"
+#include "accl/cuda/devtypes.hpp"
+#include "accl/cuda/launch.hpp"
+#include "accl/cuda/plan.hpp"
+#include "accl/cuda/symheap.hpp"
+#include "accl/request.hpp"
+
+namespace pybind11 {
+class module_;
+}
+
+namespace accl {
+namespace cuda {
+
+struct CudaConfig {
+  int device = 0;
+  size_t heap_bytes = 1ull << 30;
+  bool multicast = true;       // try to set up NVLS
+  int max_ctas = 32;           // CTAs a single call may use (== sync channels used)
+  int nvls_min_ranks = 3;      // below this, peer loads/stores beat the switch round trip
+  size_t oneshot_max_bytes = 512 << 10; // allreduce: pull-everything one-shot up to this size
+  bool engine = false;         // route calls through the persistent engine kernel
+  int engine_idle_us = 200;    // engine kernel parks itself after this idle time (0 = never)
+};
+
+class CudaDevice;
+
+struct CudaRequest : public BaseRequest {
+  using BaseRequest::BaseRequest;
+  ~CudaRequest() override;
+  CudaDevice *dev = nullptr;
+  cudaEvent_t done = nullptr;
+  uint32_t slot = 0, seq = 0;
+  bool immediate = false; // completed on the host (config calls)
+  std::vector<std::shared_ptr<BufferStorage>> temps; // staging buffers that live as long as the call
+  std::vector<std::pair<BaseBuffer *, std::shared_ptr<BufferStorage>>> copy_out;
+  void wait() override;
+  bool wait(std::chrono::milliseconds timeout) override;
+  bool test() override;
+  void finish();
+};
+
+class CudaDevice : public CCLO {
+public:
+  CudaDevice(std::shared_ptr<Oob> oob, const CudaConfig &cfg);
+  ~CudaDevice() override;
+
+  ACCLRequest *call(const Options &options) override;
+  ACCLRequest *start(const Options &options) override;
+  val_t read(addr_t offset) override;
+  void write(addr_t offset, val_t val) override;
+  void wait(ACCLRequest *request) override;
+  bool wait(ACCLRequest *request, std::chrono::milliseconds timeout) override;
+  bool test(ACCLRequest *request) override;
+  void free_request(ACCLRequest *request) override;
+  val_t get_retcode(ACCLRequest *request) override;
+  uint64_t get_duration(ACCLRequest *request) override;
+  deviceType get_device_type() override { return deviceType::cuda; }
+  std::string describe() override;
+  void printDebug() override;
+  std::string debug_state();
+  std::shared_ptr<BufferStorage> allocate(size_t bytes, bufferKind kind) override;
+  std::shared_ptr<BufferStorage> wrap_host(void *host_ptr, size_t bytes) override;
+  void attach(int world_size, int local_rank) override;
+
+  // ---- CUDA specifics
+  const DevWorld &world() const { return world_; }
+  SymHeap &heap() { return *heap_; }
+  const CudaConfig &config() const { return cfg_; }
+  cudaStream_t stream() const { return stream_; }
+  // stream of the current call sequence (user stream if one was set)
+  cudaStream_t op_stream() const { return op_stream_ ? op_stream_ : stream_; }
+  void set_stream(void *s) override { op_stream_ = static_cast<cudaStream_t>(s); }
+  int device() const { return cfg_.device; }
+  bool has_multicast() const { return heap_->has_multicast(); }
+  RangeAllocator &allocator() { return *alloc_; }
+  HostCompletion *host_completions() { return hc_host_; }
+  struct PlanCfg plan_cfg() const;
+  bool build_work_item(const Options &o, const CallDesc &d, WorkItem &w, uint32_t &err);
+  uint32_t timeout_us() const;
+  Oob &oob() { return *oob_; }
+
+private:
+  uint32_t host_config(const CallDesc &d);
+  void setup_eager_area();
+  void sync_ctrl_word(uint32_t byte_off);
+
+  std::shared_ptr<Oob> oob_;
+  CudaConfig cfg_;
+  std::unique_ptr<SymHeap> heap_;
+  std::unique_ptr<RangeAllocator> alloc_;
+  DevWorld world_{};
+  cudaStream_t stream_ = nullptr;
+  cudaStream_t op_stream_ = nullptr;
+  std::vector<uint32_t> shadow_; // host copy of exchange memory
+  HostCompletion *hc_host_ = nullptr, *hc_dev_ = nullptr;
+  std::vector<std::shared_ptr<CudaRequest>> slot_owner_;
+  uint32_t next_slot_ = 0, next_seq_ = 1;
+  uint64_t egr_area_off_ = 0;
+  std::mutex m_;
+  RequestRegistry requests_;
+  std::shared_ptr<BufferStorage> egr_area_;
+  friend struct CudaRequest;
+  friend class Engine;
+  std::unique_ptr<class Engine> engine_;
+};
+
+// In-process world: N ranks as threads of this process, rank i on devices[i]
+// (devices may repeat: several ranks share one GPU, without NVLS).
+std::vector<std::unique_ptr<CudaDevice>> make_local_world(const std::vector<int> &devices, const CudaConfig &base);
+
+void bind_cuda(pybind11::module_ &m);
+
+} // namespace cuda
+} // namespace accl

@@ -1,0 +1,24 @@
+// Host-callable entry points of the CUDA translation units (kernel launches).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "accl/cuda/devtypes.hpp"
+
+namespace accl {
+namespace cuda {
+
+// host-visible mirror of a finished call (pinned, written by the last CTA)
+struct HostCompletion {
+  volatile uint32_t retcode;
+  volatile uint32_t seq;
+  volatile unsigned long long t_start, t_end;
+};
+
+// one call, one kernel: `item.n_ctas` CTAs cooperate, completion goes to hc (device-visible pinned pointer)
+cudaError_t launch_call(const DevWorld &w, const WorkItem &item, HostCompletion *hc_dev, cudaStream_t stream);
+
+// zero the protocol state of my control block (soft reset)
+cudaError_t launch_reset_ctrl(const DevWorld &w, cudaStream_t stream);
+
+} // namespace cuda
+} // namespace accl

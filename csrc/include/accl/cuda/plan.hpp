@@ -1,0 +1,118 @@
+// Call planning shared by the host (direct launches, host ring) and the
+// engine's control CTA (device-issued commands): decode communicator and
+// arithmetic configuration from exchange memory, pick protocol, algorithm and
+// CTA count.  Must be a pure function of the call and of configuration that
+// is identical on all ranks, because both ends of every transfer derive their
+// behaviour from it independently.
+//
+// Reference: the per-call decisions at the top of every firmware collective
+// (eager vs rendezvous: ccl_offload_control.c:587,667,808,1009,1142,1314,1523,
+// 1768,1878; tree/flat selection from the tuning registers, accl.cpp:1198-1208).
+// On an NVSwitch domain the choices are eager-slots / one-shot / two-shot and
+// in-switch (NVLS) vs peer load-store instead of ring / flat / binary tree.
+#pragma once
+#include "accl/cuda/devtypes.hpp"
+
+namespace accl {
+namespace cuda {
+
+struct PlanCfg {
+  uint32_t max_ctas;
+  uint32_t nvls_min_ranks;
+  uint32_t has_mc;
+  uint32_t heap_world;
+  uint64_t oneshot_max_bytes;
+};
+
+ACCL_HD uint32_t plan_ctas(uint64_t bytes, uint64_t per_cta, uint32_t cap) {
+  uint64_t n = (bytes + per_cta - 1) / per_cta;
+  if (n < 1) n = 1;
+  if (n > cap) n = cap;
+  return static_cast<uint32_t>(n);
+}
+
+ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
+  const operation op = static_cast<operation>(w.desc.scenario);
+  const uint64_t ubytes = static_cast<uint64_t>(w.desc.count) * dtype_bytes(static_cast<dataType>(w.udtype));
+  const uint32_t P = w.comm_size;
+  const uint32_t cap = cfg.max_ctas < static_cast<uint32_t>(MAX_CH) ? cfg.max_ctas : static_cast<uint32_t>(MAX_CH);
+  w.flags = cfg.has_mc ? WF_USE_MC : 0;
+  if (op == operation::nop || op == operation::config) {
+    w.algo = ALGO_LOCAL;
+    w.n_ctas = 1;
+    return;
+  }
+  if (op == operation::copy || op == operation::combine) {
+    w.algo = ALGO_LOCAL;
+    w.n_ctas = plan_ctas(ubytes, 64u << 10, cap);
+    return;
+  }
+  if (op == operation::barrier) {
+    w.algo = ALGO_P2P;
+    w.n_ctas = 1;
+    return;
+  }
+  uint64_t moved = ubytes; // payload a rank moves, for sizing
+  if (op == operation::allgather || op == operation::reduce_scatter || op == operation::alltoall ||
+      op == operation::scatter || op == operation::gather)
+    moved = ubytes * P;
+  const bool compressed = w.desc.compression_flags != 0;
+  const bool eager = compressed || ubytes <= exch[exchmem::MAX_EAGER_SIZE / 4];
+  if (eager) {
+    w.algo = ALGO_EAGER;
+    const uint32_t ecap = cap < static_cast<uint32_t>(EGR_CH) ? cap : static_cast<uint32_t>(EGR_CH);
+    w.n_ctas = (op == operation::send || op == operation::recv) ? 1 : plan_ctas(ubytes, 16u << 10, ecap);
+    return;
+  }
+  const bool nvls = cfg.has_mc && P >= cfg.nvls_min_ranks && P == cfg.heap_world;
+  w.algo = nvls ? ALGO_NVLS : ALGO_P2P;
+  if (op == operation::allreduce && ubytes <= cfg.oneshot_max_bytes) w.algo = ALGO_P2P_ONESHOT;
+  if (op == operation::send || op == operation::recv) w.algo = ALGO_P2P;
+  w.n_ctas = plan_ctas(moved, 128u << 10, cap);
+}
+
+// Decode + plan.  Returns an error word (0 = ok).
+ACCL_HD uint32_t build_work_item_hd(const uint32_t *exch, const PlanCfg &cfg, uint32_t world, const CallDesc &d,
+                                    uint32_t timeout_us, WorkItem &w) {
+  w.desc = d;
+  w.scratch_off = 0;
+  w.scratch_bytes = 0;
+  w.req_slot = 0;
+  w.req_seq = 0;
+  const uint32_t ci = d.comm;
+  if (ci >= static_cast<uint32_t>(ACCL_MAX_COMMUNICATORS)) return CONFIG_SWITCH_ERROR;
+  w.comm_size = exch[exchmem::comm_offset(ci) / 4];
+  w.comm_rank = exch[exchmem::comm_offset(ci) / 4 + 1];
+  if (w.comm_size == 0 || w.comm_size > static_cast<uint32_t>(ACCL_MAX_RANKS)) return CONFIG_SWITCH_ERROR;
+  for (uint32_t r = 0; r < static_cast<uint32_t>(ACCL_MAX_RANKS); ++r) {
+    uint32_t g = 0;
+    if (r < w.comm_size) {
+      g = exch[exchmem::comm_rank_offset(ci, r, exchmem::CR_SESSION) / 4];
+      if (g >= world) return CONFIG_SWITCH_ERROR;
+    }
+    w.members[r] = static_cast<uint8_t>(g);
+  }
+  if (d.arithcfg >= exchmem::MAX_ARITHCFG) return ARITH_ERROR;
+  const uint32_t ab = exchmem::arith_offset(d.arithcfg, 0) / 4;
+  w.udtype = exch[ab + exchmem::AC_UNCOMPRESSED_BYTES] >> 16;
+  w.cdtype = exch[ab + exchmem::AC_COMPRESSED_BYTES] >> 16;
+  w.ratio_log = exch[ab + exchmem::AC_RATIO_LOG];
+  w.arith_compressed = exch[ab + exchmem::AC_ARITH_COMPRESSED];
+  w.timeout_us = timeout_us;
+  const operation op = static_cast<operation>(d.scenario);
+  const bool rooted = op == operation::send || op == operation::recv || op == operation::bcast ||
+                      op == operation::scatter || op == operation::gather || op == operation::reduce;
+  if (rooted && d.root_src_dst >= w.comm_size) return CONFIG_SWITCH_ERROR;
+  // a communicator of one: every collective degenerates to a local copy
+  if (w.comm_size == 1 && op != operation::copy && op != operation::combine && op != operation::nop &&
+      op != operation::config) {
+    if (op == operation::barrier || op == operation::bcast) w.desc.scenario = static_cast<uint32_t>(operation::nop);
+    else if (op == operation::send || op == operation::recv) return CONFIG_SWITCH_ERROR; // no loop-back slots to self
+    else w.desc.scenario = static_cast<uint32_t>(operation::copy);
+  }
+  plan_call(exch, cfg, w);
+  return 0;
+}
+
+} // namespace cuda
+} // namespace accl

@@ -78,6 +78,25 @@ __device__ __forceinline__ uint32_t atom_add_acqrel_gpu(uint32_t *p, uint32_t v)
   asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
   return old;
 }
+// `unsigned long long` flavours (CUDA atomics use that type; uint64_t is `unsigned long` on LP64)
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  return ld_acquire_sys(reinterpret_cast<const uint64_t *>(p));
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+  return ld_relaxed_sys(reinterpret_cast<const uint64_t *>(p));
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
+  return ld_acquire_gpu(reinterpret_cast<const uint64_t *>(p));
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  st_release_sys(reinterpret_cast<uint64_t *>(p), static_cast<uint64_t>(v));
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  st_relaxed_sys(reinterpret_cast<uint64_t *>(p), static_cast<uint64_t>(v));
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v) {
+  st_release_gpu(reinterpret_cast<uint64_t *>(p), static_cast<uint64_t>(v));
+}
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void fence_sc_sys() { asm volatile("fence.sc.sys;" ::: "memory"); }
 __device__ __forceinline__ uint64_t globaltimer_ns() {

@@ -1,0 +1,59 @@
+// pybind11 glue for the CUDA backend (kept out of pyaccl.cpp so that the
+// emulator-only build has no CUDA dependency).
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "accl/accl.hpp"
+#include "accl/cuda/cudadevice.hpp"
+#include "accl/cuda/driver_api.hpp"
+
+namespace py = pybind11;
+
+namespace accl {
+namespace cuda {
+
+static CudaConfig make_cfg(int device, size_t heap_mb, bool multicast, int max_ctas, bool engine, int nvls_min_ranks,
+                           size_t oneshot_kb) {
+  CudaConfig c;
+  c.device = device;
+  c.heap_bytes = heap_mb << 20;
+  c.multicast = multicast;
+  c.max_ctas = max_ctas;
+  c.engine = engine;
+  c.nvls_min_ranks = nvls_min_ranks;
+  c.oneshot_max_bytes = oneshot_kb << 10;
+  return c;
+}
+
+void bind_cuda(py::module_ &m) {
+  m.def("cuda_driver_available", [] { return DriverApi::available(); });
+  m.def("cuda_debug_state", [](ACCL &a) {
+    auto *d = dynamic_cast<CudaDevice *>(a.device());
+    if (!d) throw std::runtime_error("not a CUDA backend");
+    return d->debug_state();
+  });
+  m.def("cuda_probe", [](int device) { return probe_topology(device).describe(); });
+  // N ranks in this process (threads), rank i on devices[i]
+  m.def("make_cuda_world", [](std::vector<int> devices, size_t heap_mb, bool multicast, int max_ctas, bool engine,
+                              int nvls_min_ranks, size_t oneshot_kb) {
+    std::vector<std::unique_ptr<ACCL>> out;
+    auto devs = make_local_world(devices, make_cfg(0, heap_mb, multicast, max_ctas, engine, nvls_min_ranks, oneshot_kb));
+    for (auto &d : devs) out.emplace_back(new ACCL(std::move(d)));
+    return out;
+  }, py::arg("devices"), py::arg("heap_mb") = 256, py::arg("multicast") = true, py::arg("max_ctas") = 32,
+        py::arg("engine") = false, py::arg("nvls_min_ranks") = 3, py::arg("oneshot_kb") = 512,
+        py::call_guard<py::gil_scoped_release>());
+  // one rank per process; bootstrap over a private TCP rendezvous on addr:port
+  m.def("make_cuda_rank", [](int rank, int world, int device, const std::string &addr, int port, size_t heap_mb,
+                             bool multicast, int max_ctas, bool engine, int nvls_min_ranks, size_t oneshot_kb) {
+    auto oob = std::make_shared<TcpOob>(rank, world, addr, port);
+    auto dev = std::unique_ptr<CCLO>(
+        new CudaDevice(oob, make_cfg(device, heap_mb, multicast, max_ctas, engine, nvls_min_ranks, oneshot_kb)));
+    return std::unique_ptr<ACCL>(new ACCL(std::move(dev)));
+  }, py::arg("rank"), py::arg("world_size"), py::arg("device"), py::arg("addr") = "127.0.0.1", py::arg("port") = 29637,
+        py::arg("heap_mb") = 1024, py::arg("multicast") = true, py::arg("max_ctas") = 32, py::arg("engine") = false,
+        py::arg("nvls_min_ranks") = 3, py::arg("oneshot_kb") = 512, py::call_guard<py::gil_scoped_release>());
+}
+
+} // namespace cuda
+} // namespace accl

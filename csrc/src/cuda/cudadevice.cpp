@@ -1,0 +1,501 @@
+#include "accl/cuda/cudadevice.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <sstream>
+#include <thread>
+
+#include "accl/common.hpp"
+#include "accl/cuda/driver_api.hpp"
+#include "accl/cuda/engine.hpp"
+#include "accl/cuda/plan.hpp"
+
+namespace accl {
+namespace cuda {
+
+// ------------------------------------------------------------------ storage
+namespace {
+// Process-wide cache of pinned host blocks.  cudaFreeHost synchronises the
+// whole device: doing that while a peer rank's kernel on the same GPU spins on
+// a flag this thread has yet to raise is a deadlock, so blocks are recycled
+// instead of returned to the driver.
+class PinnedPool {
+public:
+  static PinnedPool &get() {
+    static PinnedPool *p = new PinnedPool(); // intentionally leaked: outlives every CUDA context user
+    return *p;
+  }
+  void *alloc(size_t bytes, size_t &cap) {
+    cap = 256;
+    while (cap < bytes) cap <<= 1;
+    {
+      std::lock_guard<std::mutex> g(m_);
+      auto &fl = free_[cap];
+      if (!fl.empty()) {
+        void *p = fl.back();
+        fl.pop_back();
+        return p;
+      }
+    }
+    void *p = nullptr;
+    ACCL_CUDART(cudaHostAlloc(&p, cap, cudaHostAllocPortable));
+    return p;
+  }
+  void release(void *p, size_t cap) {
+    std::lock_guard<std::mutex> g(m_);
+    free_[cap].push_back(p);
+  }
+
+private:
+  std::mutex m_;
+  std::map<size_t, std::vector<void *>> free_;
+};
+
+class CudaStorage : public BufferStorage {
+public:
+  CudaStorage(CudaDevice *d, size_t bytes, bufferKind kind, void *wrap)
+      : dev_(d), bytes_(bytes), kind_(kind), wrapped_(wrap) {
+    if (kind != bufferKind::host_only) off_ = d->allocator().alloc(std::max<size_t>(bytes, 16), 256);
+    else ensure_host();
+  }
+  ~CudaStorage() override {
+    cudaSetDevice(dev_->device());
+    if (kind_ != bufferKind::host_only) {
+      // the engine may still be reading: drain the backend stream first
+      cudaStreamSynchronize(dev_->stream());
+      try {
+        dev_->allocator().free(off_);
+      } catch (...) {
+      }
+    }
+    if (pinned_) PinnedPool::get().release(pinned_, pinned_cap_);
+  }
+  void *host_ptr() override {
+    if (wrapped_) return wrapped_;
+    ensure_host();
+    return pinned_;
+  }
+  addr_t device_addr() const override { return kind_ == bufferKind::host_only ? 0 : off_; }
+  void *device_ptr() const override {
+    return kind_ == bufferKind::host_only ? nullptr : dev_->heap().local() + off_;
+  }
+  size_t bytes() const override { return bytes_; }
+  bufferKind kind() const override { return kind_; }
+  void to_device(size_t off, size_t len) override {
+    if (kind_ == bufferKind::host_only || len == 0) return;
+    cudaSetDevice(dev_->device());
+    ACCL_CUDART(cudaMemcpyAsync(dev_->heap().local() + off_ + off, static_cast<char *>(host_ptr()) + off, len,
+                                cudaMemcpyHostToDevice, dev_->op_stream()));
+  }
+  void from_device(size_t off, size_t len) override {
+    if (kind_ == bufferKind::host_only || len == 0) return;
+    cudaSetDevice(dev_->device());
+    ACCL_CUDART(cudaMemcpyAsync(static_cast<char *>(host_ptr()) + off, dev_->heap().local() + off_ + off, len,
+                                cudaMemcpyDeviceToHost, dev_->op_stream()));
+    ACCL_CUDART(cudaStreamSynchronize(dev_->op_stream()));
+  }
+  bool is_simulated() const override { return false; }
+
+private:
+  void ensure_host() {
+    if (wrapped_ || pinned_) return;
+    cudaSetDevice(dev_->device());
+    pinned_ = PinnedPool::get().alloc(std::max<size_t>(bytes_, 16), pinned_cap_);
+    std::memset(pinned_, 0, bytes_);
+  }
+  CudaDevice *dev_;
+  size_t bytes_;
+  bufferKind kind_;
+  uint64_t off_ = 0;
+  void *pinned_ = nullptr;
+  size_t pinned_cap_ = 0;
+  void *wrapped_ = nullptr;
+};
+} // namespace
+
+// ------------------------------------------------------------------ request
+CudaRequest::~CudaRequest() {
+  if (done) cudaEventDestroy(done);
+}
+
+void CudaRequest::finish() {
+  if (status() == operationStatus::COMPLETED) return;
+  HostCompletion *hc = &dev->hc_host_[slot];
+  const uint32_t rc = hc->seq == seq ? hc->retcode : static_cast<uint32_t>(DMA_INTERNAL_ERROR);
+  const uint64_t dur = hc->t_end > hc->t_start ? hc->t_end - hc->t_start : 0;
+  for (auto &co : copy_out) { // results of host-resident operands
+    co.second->from_device(0, co.second->bytes());
+    if (co.first && co.first->byte_array()) std::memcpy(co.first->byte_array(), co.second->host_ptr(), co.first->size());
+  }
+  temps.clear();
+  copy_out.clear();
+  complete(rc, dur);
+}
+
+void CudaRequest::wait() {
+  if (status() == operationStatus::COMPLETED) return;
+  if (!immediate) {
+    cudaSetDevice(dev->device());
+    cudaError_t e = cudaEventSynchronize(done);
+    if (e != cudaSuccess) {
+      complete(DMA_INTERNAL_ERROR, 0);
+      throw std::runtime_error(std::string("CUDA error while waiting for a call: ") + cudaGetErrorString(e));
+    }
+  }
+  finish();
+}
+
+bool CudaRequest::wait(std::chrono::milliseconds timeout) {
+  auto deadline = std::chrono::steady_clock::now() + timeout;
+  while (!test()) {
+    if (std::chrono::steady_clock::now() > deadline) return false;
+    std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
+  return true;
+}
+
+bool CudaRequest::test() {
+  if (status() == operationStatus::COMPLETED) return true;
+  if (!immediate) {
+    cudaSetDevice(dev->device());
+    if (cudaEventQuery(done) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return false;
+    }
+  }
+  finish();
+  return true;
+}
+
+// ------------------------------------------------------------------- device
+CudaDevice::CudaDevice(std::shared_ptr<Oob> oob, const CudaConfig &cfg) : oob_(std::move(oob)), cfg_(cfg) {
+  ACCL_CUDART(cudaSetDevice(cfg_.device));
+  heap_.reset(new SymHeap(*oob_, cfg_.device, cfg_.heap_bytes, cfg_.multicast));
+  if (heap_->bytes() < CTRL_BYTES * 2) throw std::runtime_error("symmetric heap too small");
+  alloc_.reset(new RangeAllocator(CTRL_BYTES, heap_->bytes() - CTRL_BYTES));
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  ACCL_CUDART(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, prio_hi));
+  world_.window = heap_->window();
+  world_.mc = heap_->mc_base();
+  world_.heap_bytes = heap_->bytes();
+  world_.world = static_cast<uint32_t>(heap_->world());
+  world_.rank = static_cast<uint32_t>(heap_->rank());
+  shadow_.assign(exchmem::SIZE_WORDS, 0);
+  uint32_t hwid = CAP_DMA | CAP_ARITH | CAP_COMPRESSION | CAP_RENDEZVOUS | CAP_FP8 | CAP_TCGEN05 | CAP_STREAMS;
+  if (heap_->has_multicast()) hwid |= CAP_NVLS_MULTICAST;
+  if (cfg_.engine) hwid |= CAP_PERSISTENT_ENGINE;
+  shadow_[exchmem::HWID / 4] = hwid;
+  ACCL_CUDART(cudaHostAlloc(reinterpret_cast<void **>(&hc_host_), sizeof(HostCompletion) * N_REQ_SLOTS,
+                            cudaHostAllocMapped | cudaHostAllocPortable));
+  std::memset(hc_host_, 0, sizeof(HostCompletion) * N_REQ_SLOTS);
+  ACCL_CUDART(cudaHostGetDevicePointer(reinterpret_cast<void **>(&hc_dev_), hc_host_, 0));
+  slot_owner_.assign(N_REQ_SLOTS, nullptr);
+  ACCL_CUDART(launch_reset_ctrl(world_, stream_));
+  ACCL_CUDART(cudaStreamSynchronize(stream_));
+  oob_->barrier(); // nobody signals a peer whose control block is not zeroed yet
+  if (cfg_.engine) engine_.reset(new Engine(*this));
+}
+
+CudaDevice::~CudaDevice() {
+  cudaSetDevice(cfg_.device);
+  engine_.reset();
+  cudaStreamSynchronize(stream_);
+  egr_area_.reset();
+  slot_owner_.clear();
+  if (hc_host_) cudaFreeHost(hc_host_);
+  heap_.reset();
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+void CudaDevice::attach(int world_size, int local_rank) {
+  if (world_size > heap_->world()) throw std::invalid_argument("CudaDevice: more ranks than the heap was built for");
+  (void)local_rank;
+}
+
+std::string CudaDevice::describe() {
+  std::ostringstream o;
+  o << "CudaDevice rank " << heap_->rank() << "/" << heap_->world() << " gpu " << cfg_.device << " heap "
+    << (heap_->bytes() >> 20) << " MiB nvls=" << (heap_->has_multicast() ? "yes" : "no");
+  if (!heap_->has_multicast()) o << " (" << heap_->multicast_note() << ")";
+  o << " mode=" << (cfg_.engine ? "engine" : "direct") << " max_ctas=" << cfg_.max_ctas;
+  return o.str();
+}
+
+void CudaDevice::printDebug() { ACCL_ERROR_LOG(debug_state()); }
+
+// protocol counters of my control block, for post-mortems
+std::string CudaDevice::debug_state() {
+  cudaSetDevice(cfg_.device);
+  std::vector<char> buf(sizeof(Ctrl));
+  cudaMemcpy(buf.data(), heap_->local(), sizeof(Ctrl), cudaMemcpyDeviceToHost);
+  const Ctrl *c = reinterpret_cast<const Ctrl *>(buf.data());
+  std::ostringstream o;
+  o << describe() << "\n";
+  for (uint32_t p = 0; p < world_.world; ++p) {
+    if (p == world_.rank) continue;
+    o << " peer " << p << ":";
+    for (int ch = 0; ch < 4; ++ch)
+      o << " ch" << ch << "[sync sent=" << c->sent[ch][p] << " exp=" << c->expect[ch][p] << " sig=" << c->sig[ch][p]
+        << " | egr sent=" << c->egr_sent[ch][p] << " ack=" << c->egr_ack[ch][p] << " exp=" << c->egr_expect[ch][p]
+        << " sig=" << c->egr_sig[ch][p] << "]";
+    o << "\n";
+  }
+  return o.str();
+}
+
+uint32_t CudaDevice::timeout_us() const {
+  // TIMEOUT register counts units of 32 µs on this backend (1e6 -> 32 s): GPU
+  // ranks of different processes may reach their first call seconds apart
+  const uint64_t t = static_cast<uint64_t>(shadow_[exchmem::TIMEOUT / 4]) * 32;
+  return static_cast<uint32_t>(std::min<uint64_t>(t ? t : 32000000ull, 0xFFFFFFFFull));
+}
+
+val_t CudaDevice::read(addr_t off) {
+  if (off >= exchmem::SIZE_BYTES || (off & 3)) throw std::out_of_range("exchange memory read out of range");
+  // sequence counters live in the control block, not in the shadow
+  if (off >= exchmem::COMM_BASE) {
+    const uint32_t rel = static_cast<uint32_t>(off - exchmem::COMM_BASE);
+    const uint32_t ci = rel / exchmem::COMM_STRIDE, w = (rel % exchmem::COMM_STRIDE) / 4;
+    if (w >= 2) {
+      const uint32_t r = (w - 2) / exchmem::COMM_RANK_WORDS, f = (w - 2) % exchmem::COMM_RANK_WORDS;
+      if (f == exchmem::CR_INBOUND_SEQ || f == exchmem::CR_OUTBOUND_SEQ) {
+        const uint32_t g = shadow_[exchmem::comm_rank_offset(ci, r, exchmem::CR_SESSION) / 4];
+        if (g < static_cast<uint32_t>(ACCL_MAX_RANKS)) {
+          std::lock_guard<std::mutex> lk(m_);
+          cudaSetDevice(cfg_.device);
+          Ctrl *c = reinterpret_cast<Ctrl *>(heap_->local());
+          uint32_t v = 0;
+          const uint32_t *src = f == exchmem::CR_INBOUND_SEQ ? &c->egr_expect[0][g] : &c->egr_sent[0][g];
+          cudaMemcpy(&v, src, 4, cudaMemcpyDeviceToHost);
+          return v;
+        }
+      }
+    }
+  }
+  return shadow_[off / 4];
+}
+
+void CudaDevice::sync_ctrl_word(uint32_t off) {
+  cudaSetDevice(cfg_.device);
+  Ctrl *c = reinterpret_cast<Ctrl *>(heap_->local());
+  ACCL_CUDART(cudaMemcpyAsync(&c->exch[off / 4], &shadow_[off / 4], 4, cudaMemcpyHostToDevice, stream_));
+}
+
+void CudaDevice::write(addr_t off, val_t val) {
+  if (off >= exchmem::SIZE_BYTES || (off & 3)) throw std::out_of_range("exchange memory write out of range");
+  std::lock_guard<std::mutex> lk(m_);
+  shadow_[off / 4] = val;
+  // device-side readers (plugins, engine) see the same block
+  sync_ctrl_word(static_cast<uint32_t>(off));
+}
+
+std::shared_ptr<BufferStorage> CudaDevice::allocate(size_t bytes, bufferKind kind) {
+  return std::make_shared<CudaStorage>(this, bytes, kind, nullptr);
+}
+std::shared_ptr<BufferStorage> CudaDevice::wrap_host(void *host_ptr, size_t bytes) {
+  return std::make_shared<CudaStorage>(this, bytes, bufferKind::device, host_ptr);
+}
+
+// (re)build the eager slot area from the geometry in exchange memory
+void CudaDevice::setup_eager_area() {
+  const uint32_t slot = std::max<uint32_t>(16, (shadow_[exchmem::EAGER_RX_BUF_SIZE / 4] + 15) & ~15u);
+  const uint32_t depth = std::min<uint32_t>(std::max<uint32_t>(shadow_[exchmem::EAGER_RX_BUF_COUNT / 4], 2), EGR_DEPTH_MAX);
+  egr_area_.reset();
+  // fp8 block scaling appends scales: leave headroom of 1/8 + 16 bytes per slot
+  const uint32_t slot_alloc = (slot + slot / 8 + 16 + 15) & ~15u;
+  egr_area_ = allocate(egr_area_bytes(depth, slot_alloc), bufferKind::p2p);
+  world_.egr_off = egr_area_->device_addr();
+  world_.egr_depth = depth;
+  world_.egr_slot_bytes = slot_alloc;
+}
+
+uint32_t CudaDevice::host_config(const CallDesc &d) {
+  switch (static_cast<cfgFunc>(d.function)) {
+  case cfgFunc::reset_periph: {
+    cudaSetDevice(cfg_.device);
+    if (engine_) engine_->stop();
+    cudaStreamSynchronize(stream_);
+    launch_reset_ctrl(world_, stream_);
+    cudaStreamSynchronize(stream_);
+    shadow_[exchmem::CFGRDY / 4] = 0;
+    shadow_[exchmem::PKT_ENABLED / 4] = 0;
+    return 0;
+  }
+  case cfgFunc::enable_pkt:
+    if (engine_) engine_->stop(); // it restarts with the new slot geometry
+    setup_eager_area();
+    shadow_[exchmem::PKT_ENABLED / 4] = 1;
+    return 0;
+  case cfgFunc::set_timeout:
+    shadow_[exchmem::TIMEOUT / 4] = d.count;
+    return 0;
+  case cfgFunc::set_max_eager_msg_size:
+    if (d.count < shadow_[exchmem::EAGER_RX_BUF_SIZE / 4]) return EAGER_THRESHOLD_INVALID;
+    shadow_[exchmem::MAX_EAGER_SIZE / 4] = d.count;
+    return 0;
+  case cfgFunc::set_max_rendezvous_msg_size:
+    if (d.count <= shadow_[exchmem::MAX_EAGER_SIZE / 4]) return RENDEZVOUS_THRESHOLD_INVALID;
+    shadow_[exchmem::MAX_RENDEZVOUS_SIZE / 4] = d.count;
+    return 0;
+  }
+  return COLLECTIVE_NOT_IMPLEMENTED;
+}
+
+PlanCfg CudaDevice::plan_cfg() const {
+  PlanCfg c;
+  c.max_ctas = static_cast<uint32_t>(cfg_.max_ctas);
+  c.nvls_min_ranks = static_cast<uint32_t>(cfg_.nvls_min_ranks);
+  c.has_mc = heap_->has_multicast() ? 1u : 0u;
+  c.heap_world = static_cast<uint32_t>(heap_->world());
+  c.oneshot_max_bytes = cfg_.oneshot_max_bytes;
+  return c;
+}
+
+bool CudaDevice::build_work_item(const Options &o, const CallDesc &d, WorkItem &w, uint32_t &err) {
+  (void)o;
+  std::memset(&w, 0, sizeof(w));
+  const uint32_t e = build_work_item_hd(shadow_.data(), plan_cfg(), world_.world, d, timeout_us(), w);
+  err |= e;
+  return e == 0;
+}
+
+ACCLRequest *CudaDevice::start(const Options &options) {
+  for (ACCLRequest *dep : options.waitfor)
+    if (dep) wait(dep);
+  auto req = std::make_shared<CudaRequest>(options);
+  req->dev = this;
+  req->desc = make_call_desc(options);
+  ACCLRequest *h = requests_.add(req);
+  std::lock_guard<std::mutex> lk(m_);
+  ACCL_CUDART(cudaSetDevice(cfg_.device));
+  if (options.scenario == operation::config) {
+    req->immediate = true;
+    const uint32_t rc = host_config(req->desc);
+    shadow_[exchmem::RETCODE / 4] = rc;
+    req->complete(rc, 0);
+    return h;
+  }
+  if (options.stream_flags != streamFlags::NO_STREAM) {
+    req->immediate = true;
+    req->complete(COLLECTIVE_NOT_IMPLEMENTED, 0);
+    return h;
+  }
+  cudaStream_t s = options.stream ? static_cast<cudaStream_t>(options.stream) : op_stream();
+  // ---- host-resident operands are staged through heap scratch
+  Options o = options;
+  std::unique_ptr<BaseBuffer> tmp_bufs[3];
+  BaseBuffer **ops[3] = {&o.addr_0, &o.addr_1, &o.addr_2};
+  const hostFlags hbits[3] = {hostFlags::OP0_HOST, hostFlags::OP1_HOST, hostFlags::RES_HOST};
+  for (int i = 0; i < 3; ++i) {
+    if (!any(options.host_flags & hbits[i]) || !*ops[i] || (*ops[i])->is_dummy()) continue;
+    BaseBuffer *hb = *ops[i];
+    auto st = allocate(hb->size(), bufferKind::device);
+    req->temps.push_back(st);
+    tmp_bufs[i].reset(new BaseBuffer(st, 0, hb->size(), hb->type()));
+    if (i < 2) {
+      ACCL_CUDART(cudaMemcpyAsync(st->device_ptr(), hb->byte_array(), hb->size(), cudaMemcpyHostToDevice, s));
+    } else {
+      req->copy_out.emplace_back(hb, st);
+    }
+    *ops[i] = tmp_bufs[i].get();
+  }
+  if (!req->temps.empty()) req->desc = make_call_desc(o);
+
+  WorkItem w;
+  uint32_t err = 0;
+  if (!build_work_item(o, req->desc, w, err)) {
+    req->immediate = true;
+    req->complete(err ? err : static_cast<uint32_t>(CONFIG_SWITCH_ERROR), 0);
+    return h;
+  }
+  // ---- completion slot
+  const uint32_t slot = next_slot_++ % (N_REQ_SLOTS - 1); // the last record belongs to device-issued calls
+  if (slot_owner_[slot]) slot_owner_[slot]->wait(); // ring wrapped: the old occupant must be done
+  slot_owner_[slot] = req;
+  req->slot = slot;
+  req->seq = next_seq_++;
+  if (next_seq_ == 0) next_seq_ = 1;
+  w.req_slot = slot;
+  w.req_seq = req->seq;
+  ACCL_CUDART(cudaEventCreateWithFlags(&req->done, cudaEventDisableTiming));
+  if (engine_) engine_->submit(w, &hc_dev_[slot], s);
+  else ACCL_CUDART(launch_call(world_, w, &hc_dev_[slot], s));
+  ACCL_CUDART(cudaEventRecord(req->done, s));
+  req->set_status(operationStatus::EXECUTING);
+  return h;
+}
+
+ACCLRequest *CudaDevice::call(const Options &options) {
+  ACCLRequest *h = start(options);
+  wait(h);
+  return h;
+}
+
+void CudaDevice::wait(ACCLRequest *request) {
+  auto r = requests_.find(request);
+  if (!r) throw std::invalid_argument("wait: unknown request");
+  r->wait();
+}
+bool CudaDevice::wait(ACCLRequest *request, std::chrono::milliseconds timeout) {
+  auto r = requests_.find(request);
+  if (!r) throw std::invalid_argument("wait: unknown request");
+  return r->wait(timeout);
+}
+bool CudaDevice::test(ACCLRequest *request) {
+  auto r = requests_.find(request);
+  if (!r) throw std::invalid_argument("test: unknown request");
+  return r->test();
+}
+void CudaDevice::free_request(ACCLRequest *request) {
+  auto r = std::dynamic_pointer_cast<CudaRequest>(requests_.find(request));
+  if (r) {
+    std::lock_guard<std::mutex> lk(m_);
+    if (r->status() != operationStatus::COMPLETED) {
+      // still in flight: keep the slot owner alive, drop only the user handle
+    } else {
+      if (slot_owner_[r->slot] == r) slot_owner_[r->slot] = nullptr;
+      if (r->done) {
+        cudaEventDestroy(r->done);
+        r->done = nullptr;
+      }
+    }
+  }
+  requests_.erase(request);
+}
+val_t CudaDevice::get_retcode(ACCLRequest *request) {
+  auto r = requests_.find(request);
+  if (!r) throw std::invalid_argument("get_retcode: unknown request");
+  return r->retcode();
+}
+uint64_t CudaDevice::get_duration(ACCLRequest *request) {
+  auto r = requests_.find(request);
+  if (!r) throw std::invalid_argument("get_duration: unknown request");
+  return r->duration_ns();
+}
+
+std::vector<std::unique_ptr<CudaDevice>> make_local_world(const std::vector<int> &devices, const CudaConfig &base) {
+  const int W = static_cast<int>(devices.size());
+  auto oobs = LocalOob::create(W);
+  std::vector<std::unique_ptr<CudaDevice>> out(static_cast<size_t>(W));
+  std::vector<std::string> errs(static_cast<size_t>(W));
+  std::vector<std::thread> ts;
+  for (int r = 0; r < W; ++r)
+    ts.emplace_back([&, r] {
+      try {
+        CudaConfig c = base;
+        c.device = devices[static_cast<size_t>(r)];
+        out[static_cast<size_t>(r)].reset(new CudaDevice(oobs[static_cast<size_t>(r)], c));
+      } catch (const std::exception &e) {
+        errs[static_cast<size_t>(r)] = e.what();
+      }
+    });
+  for (auto &t : ts) t.join();
+  for (auto &e : errs)
+    if (!e.empty()) throw std::runtime_error("make_local_world: " + e);
+  return out;
+}
+
+} // namespace cuda
+} // namespace accl

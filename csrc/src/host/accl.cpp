@@ -127,6 +127,9 @@ void ACCL::setup_eager_rx_buffers(size_t n, addr_t size) {
 }
 
 void ACCL::setup_rendezvous_spare_buffers(addr_t size) {
+  // scratch for tree reductions / staging; engines chunk through it, so cap it
+  // like the reference's bring-up code does (accl_network_utils.cpp:521: 4 MB)
+  size = std::min<addr_t>(size, 4u << 20);
   spare_buffers.clear();
   cclo->write(exchmem::SPARE_BUF_SIZE, static_cast<val_t>(size));
   for (uint32_t i = 0; i < exchmem::NUM_SPARE_BUFS; ++i) {
