@@ -18,7 +18,7 @@ namespace accl {
 namespace cuda {
 
 constexpr int MAX_CH = 64;        // sync channels == max CTAs cooperating on one call
-constexpr int EGR_CH = 8;         // channels usable by eager (slot-based) transfers
+constexpr int EGR_CH = 16;        // channels usable by eager (slot-based) transfers
 constexpr int EGR_DEPTH_MAX = 16; // slots per (channel, src): the eager RX buffers
 constexpr int N_REQ_SLOTS = 256;  // completion records
 constexpr int RING_SLOTS = 128;   // command ring depth (host ring and device ring each)
@@ -125,10 +125,10 @@ enum WorkFlags : uint32_t { WF_USE_MC = 1u << 0, WF_ENGINE = 1u << 1 };
 
 // eager slot addressing inside a heap
 ACCL_HD uint64_t egr_slot_off(const DevWorld &w, uint32_t ch, uint32_t slot, uint32_t src) {
-  return w.egr_off + ((static_cast<uint64_t>(ch) * w.egr_depth + slot) * ACCL_MAX_RANKS + src) * w.egr_slot_bytes;
+  return w.egr_off + ((static_cast<uint64_t>(ch) * w.egr_depth + slot) * w.world + src) * w.egr_slot_bytes;
 }
-ACCL_HD uint64_t egr_area_bytes(uint32_t depth, uint32_t slot_bytes) {
-  return static_cast<uint64_t>(EGR_CH) * depth * ACCL_MAX_RANKS * slot_bytes;
+ACCL_HD uint64_t egr_area_bytes(uint32_t world, uint32_t depth, uint32_t slot_bytes) {
+  return static_cast<uint64_t>(EGR_CH) * depth * world * slot_bytes;
 }
 
 } // namespace cuda

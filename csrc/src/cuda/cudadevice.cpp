@@ -305,7 +305,7 @@ void CudaDevice::setup_eager_area() {
   egr_area_.reset();
   // fp8 block scaling appends scales: leave headroom of 1/8 + 16 bytes per slot
   const uint32_t slot_alloc = (slot + slot / 8 + 16 + 15) & ~15u;
-  egr_area_ = allocate(egr_area_bytes(depth, slot_alloc), bufferKind::p2p);
+  egr_area_ = allocate(egr_area_bytes(world_.world, depth, slot_alloc), bufferKind::p2p);
   world_.egr_off = egr_area_->device_addr();
   world_.egr_depth = depth;
   world_.egr_slot_bytes = slot_alloc;

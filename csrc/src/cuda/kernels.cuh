@@ -224,29 +224,32 @@ __device__ __forceinline__ void reduce_core(const PtrTable &t, int np_rt, int nd
       const char *sp[NP > 0 ? NP : 1];
 #pragma unroll
       for (int p = 0; p < NP; ++p) sp[p] = t.src[p];
+      // vectors per thread in flight: enough bytes outstanding to cover the NVLink round trip
+      constexpr int U = NP <= 2 ? 4 : (NP <= 4 ? 2 : 1);
       size_t i = tid;
-      for (; i + stride < nvec; i += 2 * stride) { // two vectors per thread in flight
-        Vec16 a[NP > 0 ? NP : 1], b[NP > 0 ? NP : 1];
+      for (; i + (U - 1) * stride < nvec; i += U * stride) {
+        Vec16 in[U][NP > 0 ? NP : 1];
 #pragma unroll
-        for (int p = 0; p < NP; ++p) a[p] = ld_relaxed_sys16(sp[p] + i * 16);
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int p = 0; p < NP; ++p) b[p] = ld_relaxed_sys16(sp[p] + (i + stride) * 16);
-        typename V::A acc[V::N], x[V::N], acc2[V::N];
-        V::unpack(a[0], acc);
-        V::unpack(b[0], acc2);
+          for (int p = 0; p < NP; ++p) in[u][p] = ld_relaxed_sys16(sp[p] + (i + u * stride) * 16);
+        Vec16 out[U];
 #pragma unroll
-        for (int p = 1; p < NP; ++p) {
-          V::unpack(a[p], x);
+        for (int u = 0; u < U; ++u) {
+          typename V::A acc[V::N], x[V::N];
+          V::unpack(in[u][0], acc);
 #pragma unroll
-          for (int e = 0; e < V::N; ++e) acc[e] = Op::apply(acc[e], x[e]);
-          V::unpack(b[p], x);
+          for (int p = 1; p < NP; ++p) {
+            V::unpack(in[u][p], x);
 #pragma unroll
-          for (int e = 0; e < V::N; ++e) acc2[e] = Op::apply(acc2[e], x[e]);
+            for (int e = 0; e < V::N; ++e) acc[e] = Op::apply(acc[e], x[e]);
+          }
+          out[u] = V::pack(acc);
         }
-        const Vec16 o1 = V::pack(acc), o2 = V::pack(acc2);
         for (int q = 0; q < ndst; ++q) {
-          st_relaxed_sys16(t.dst[q] + i * 16, o1);
-          st_relaxed_sys16(t.dst[q] + (i + stride) * 16, o2);
+          char *d = t.dst[q];
+#pragma unroll
+          for (int u = 0; u < U; ++u) st_relaxed_sys16(d + (i + u * stride) * 16, out[u]);
         }
       }
       for (; i < nvec; i += stride) {

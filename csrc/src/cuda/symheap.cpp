@@ -68,8 +68,11 @@ SymHeap::SymHeap(Oob &oob, int device, size_t bytes, bool want_multicast)
   CUdevice cudev;
   ACCL_CU(d.cuDeviceGet(&cudev, device));
   Topology topo = probe_topology(device);
-  const bool share_by_value = oob.same_process();
-  share_by_value_ = share_by_value;
+  // Handles always travel as POSIX fds (dup'ed when ranks share a process), so
+  // every rank owns its own reference to every allocation and tear-down order
+  // does not matter.
+  const bool share_by_value = false;
+  share_by_value_ = false;
 
   CUmemAllocationProp prop{};
   prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
