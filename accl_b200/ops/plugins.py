@@ -1,0 +1,48 @@
+"""Fused compute+collective plugins (CUDA backend).
+
+* gemm_reduce_scatter: row-parallel linear layer — every rank multiplies its
+  K-slice on the tcgen05 tensor cores and each finished tile is added straight
+  into the owner rank's output shard over NVLink (no intermediate C, no
+  separate reduce_scatter kernel).
+* vadd_allreduce: the vector-add plugin; the kernel computes x + y and then
+  issues the all-reduce itself through the device API (persistent engine).
+"""
+import torch
+
+from .. import _C
+from ..core import Accl, Buffer
+
+
+def _stream_handle(accl):
+    h = torch.cuda.current_stream(accl.cuda_device).cuda_stream
+    return h if h else 1  # cudaStreamLegacy
+
+
+def gemm_reduce_scatter(accl: Accl, a: torch.Tensor, w: torch.Tensor, out: Buffer = None) -> Buffer:
+    """out[M/P, N] (bf16, in the symmetric heap) = reduce_scatter over ranks of a[M, K_r] @ w[N, K_r]^T.
+
+    `a` and `w` are this rank's K-slices (bf16, contiguous, on this rank's GPU).
+    Needs M % (128 * world) == 0, N % 256 == 0, K_r % 64 == 0.  Stream ordered.
+    """
+    assert a.is_cuda and w.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert a.is_contiguous() and w.is_contiguous() and a.shape[1] == w.shape[1]
+    M, K = a.shape
+    N = w.shape[0]
+    P = accl.world
+    if out is None:
+        out = accl.create_buffer(M // P * N, torch.bfloat16)
+    assert out.length >= M // P * N
+    _C.gemm_reduce_scatter(accl.impl, a.data_ptr(), w.data_ptr(), out.impl, M, N, K, _stream_handle(accl))
+    return out
+
+
+def vadd_allreduce(accl: Accl, x: Buffer, y: Buffer, out: Buffer, tmp: Buffer = None, count: int = None):
+    """out = allreduce_sum(x + y) (fp32).  Returns a 1-element int32 CUDA tensor that receives the
+    engine's status word (0 = success) once the kernel has finished."""
+    count = x.length if count is None else count
+    if tmp is None:
+        tmp = accl.create_buffer(count, torch.float32)
+    status = torch.full((1,), -1, dtype=torch.int32, device=torch.device("cuda", accl.cuda_device))
+    _C.vadd_allreduce(accl.impl, x.impl, y.impl, tmp.impl, out.impl, count, status.data_ptr(), _stream_handle(accl))
+    status._keep = tmp
+    return status

@@ -97,6 +97,8 @@ public:
   bool build_work_item(const Options &o, const CallDesc &d, WorkItem &w, uint32_t &err);
   uint32_t timeout_us() const;
   Oob &oob() { return *oob_; }
+  class Engine *engine() { return engine_.get(); }
+  unsigned int *plugin_counter(); // zero-initialised device word for plugin kernels
 
 private:
   uint32_t host_config(const CallDesc &d);
@@ -121,6 +123,7 @@ private:
   friend struct CudaRequest;
   friend class Engine;
   std::unique_ptr<class Engine> engine_;
+  unsigned int *plugin_counter_ = nullptr;
 };
 
 // In-process world: N ranks as threads of this process, rank i on devices[i]

@@ -1,2 +1,38 @@
-// Device-API plugins (compute kernels that talk to the engine themselves).
+// Device-API plugins: compute kernels that talk to the collective machinery
+// themselves (the reference's kernels/plugins/vadd_put pattern, plus the
+// north-star tcgen05 GEMM whose epilogue feeds a reduce-scatter).
 #pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "accl/cuda/devtypes.hpp"
+
+namespace accl {
+namespace cuda {
+
+class CudaDevice;
+
+struct GemmRsArgs {
+  const void *a;     // [M, K] bf16 row-major (this rank's K-slice of the activations)
+  const void *w;     // [N, K] bf16 row-major (this rank's K-slice of the weight, nn.Linear layout)
+  uint64_t out_off;  // heap offset of this rank's [M / P, N] bf16 output shard
+  uint32_t m, n, k;
+  uint32_t epoch;    // launch counter (same on every rank), starts at 1
+};
+
+// C = A * W^T computed tile by tile on the 5th-gen tensor cores (TMA ->
+// smem -> tcgen05.mma -> TMEM); every finished accumulator tile is converted
+// to bf16 and added straight into its owner rank's output shard over NVLink
+// (red.global.add.bf16x2 on the peer-mapped heap): reduce-scatter along M with
+// no intermediate buffer and no separate collective.  Returns after enqueueing.
+cudaError_t launch_gemm_rs(CudaDevice &dev, const GemmRsArgs &args, cudaStream_t stream);
+
+// vector add whose result feeds an all-reduce issued by the kernel itself
+// through the device API (engine must be enabled): out = allreduce_sum(x + y)
+cudaError_t launch_vadd_allreduce(CudaDevice &dev, uint64_t x_off, uint64_t y_off, uint64_t tmp_off, uint64_t out_off,
+                                  uint32_t count, uint32_t comm_adr, uint32_t dpcfg_adr, uint32_t *status_dev,
+                                  cudaStream_t stream);
+
+} // namespace cuda
+} // namespace accl

@@ -6,6 +6,7 @@
 #include "accl/accl.hpp"
 #include "accl/cuda/cudadevice.hpp"
 #include "accl/cuda/driver_api.hpp"
+#include "accl/cuda/plugins.hpp"
 
 namespace py = pybind11;
 
@@ -31,6 +32,26 @@ void bind_cuda(py::module_ &m) {
     auto *d = dynamic_cast<CudaDevice *>(a.device());
     if (!d) throw std::runtime_error("not a CUDA backend");
     return d->debug_state();
+  });
+  // out_shard[M/P, N] (heap buffer, bf16) = reduce_scatter_M( A[M,K] @ W[N,K]^T ), fused on tcgen05 + NVLink
+  m.def("gemm_reduce_scatter", [](ACCL &a, uintptr_t a_ptr, uintptr_t w_ptr, BaseBuffer &out, uint32_t M, uint32_t N, uint32_t K,
+                                  uintptr_t stream) {
+    auto *d = dynamic_cast<CudaDevice *>(a.device());
+    if (!d) throw std::runtime_error("not a CUDA backend");
+    GemmRsArgs g{reinterpret_cast<const void *>(a_ptr), reinterpret_cast<const void *>(w_ptr), out.address(), M, N, K, 0};
+    cudaError_t e = launch_gemm_rs(*d, g, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) throw std::runtime_error(std::string("gemm_reduce_scatter launch: ") + cudaGetErrorString(e));
+  });
+  // out = allreduce_sum(x + y): the kernel computes and then issues the collective itself (device API -> engine)
+  m.def("vadd_allreduce", [](ACCL &a, BaseBuffer &x, BaseBuffer &y, BaseBuffer &tmp, BaseBuffer &out, uint32_t count,
+                             uintptr_t status_dev_ptr, uintptr_t stream) {
+    auto *d = dynamic_cast<CudaDevice *>(a.device());
+    if (!d) throw std::runtime_error("not a CUDA backend");
+    cudaError_t e = launch_vadd_allreduce(*d, x.address(), y.address(), tmp.address(), out.address(), count,
+                                          static_cast<uint32_t>(a.get_communicator_addr(GLOBAL_COMM)),
+                                          static_cast<uint32_t>(a.get_arithmetic_config_addr({dataType::float32, dataType::float32})),
+                                          reinterpret_cast<uint32_t *>(status_dev_ptr), reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) throw std::runtime_error(std::string("vadd_allreduce launch: ") + cudaGetErrorString(e));
   });
   m.def("cuda_probe", [](int device) { return probe_topology(device).describe(); });
   // N ranks in this process (threads), rank i on devices[i]

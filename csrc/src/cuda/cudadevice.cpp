@@ -223,6 +223,15 @@ std::string CudaDevice::describe() {
   return o.str();
 }
 
+unsigned int *CudaDevice::plugin_counter() {
+  if (!plugin_counter_) {
+    cudaSetDevice(cfg_.device);
+    ACCL_CUDART(cudaMalloc(&plugin_counter_, 64));
+    ACCL_CUDART(cudaMemset(plugin_counter_, 0, 64));
+  }
+  return plugin_counter_;
+}
+
 void CudaDevice::printDebug() { ACCL_ERROR_LOG(debug_state()); }
 
 // protocol counters of my control block, for post-mortems

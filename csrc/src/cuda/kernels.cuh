@@ -299,7 +299,7 @@ __device__ __forceinline__ void reduce_np(const PtrTable &t, int np, int ndst, s
 
 // The one place where (dtype, function) select typed code.  All threads of
 // the CTA call it with a table that is already visible (after __syncthreads).
-__device__ __noinline__ void reduce_dispatch(const PtrTable *t, int np, int ndst, size_t n, uint32_t dtype, uint32_t func,
+static __device__ __noinline__ void reduce_dispatch(const PtrTable *t, int np, int ndst, size_t n, uint32_t dtype, uint32_t func,
                                              int cta, int nctas, uint32_t *err) {
   const bool sum = func == static_cast<uint32_t>(reduceFunction::SUM);
 #define ACCL_RD(TYPE)                                                         \
@@ -320,7 +320,7 @@ __device__ __noinline__ void reduce_dispatch(const PtrTable *t, int np, int ndst
 }
 
 // byte copy t->src[0] -> t->dst[0..ndst) (push / broadcast), 16-byte path when aligned
-__device__ __noinline__ void copy_dispatch(const PtrTable *t, int ndst, size_t bytes, int cta, int nctas) {
+static __device__ __noinline__ void copy_dispatch(const PtrTable *t, int ndst, size_t bytes, int cta, int nctas) {
   const char *src = t->src[0];
   bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
   for (int q = 0; q < ndst; ++q) aligned = aligned && (reinterpret_cast<uintptr_t>(t->dst[q]) & 15) == 0;

@@ -1,0 +1,427 @@
+// GEMM -> reduce-scatter plugin (BASELINE config #5, the north-star fused path).
+//
+// Each rank holds a K-slice of a row-parallel linear layer: A_r [M, K_r] and
+// W_r [N, K_r] (bf16, K contiguous).  The full product is C = sum_r A_r W_r^T,
+// reduce-scattered along M: rank o ends up with rows [o*M/P, (o+1)*M/P).
+//
+// One persistent, warp-specialised sm_100a kernel per rank:
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of 128x64 (A) and
+//               256x64 (W) bf16 tiles, 128B-swizzled, into a 4-stage smem ring,
+//               signalling mbarriers with complete_tx
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma
+//               (cta_group::1, kind::f16, M=128 N=256 K=16) from smem
+//               descriptors into a TMEM accumulator (2 x 256 columns, double
+//               buffered); tcgen05.commit releases smem stages and publishes
+//               finished accumulators
+//   warp 2      allocates / frees TMEM
+//   warps 4-7   epilogue: tcgen05.ld the fp32 accumulator (32 lanes x 32
+//               columns per instruction), convert to bf16 and emit it with
+//               red.global.add.noftz.v4.bf16x2 directly into the OWNER rank's
+//               output shard through the peer-mapped symmetric heap — the tile
+//               goes into the collective as it leaves the tensor core
+// Tiles are visited owner-rotated (peers' rows first, own rows last) so the
+// NVLink traffic overlaps the remaining math.  Shards are zeroed in-kernel and
+// two flag barriers over the sync pads (channel MAX_CH-1) bracket the adds.
+//
+// The reference has no GEMM; its mechanism for compute-initiated communication
+// is kernels/plugins/vadd_put/vadd_put.cpp (data.push + stream_put from inside
+// the compute kernel).  Baseline to beat: cuBLAS GEMM + NCCL reduce_scatter.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <map>
+#include <mutex>
+
+#include "accl/cuda/cudadevice.hpp"
+#include "accl/cuda/driver_api.hpp"
+#include "accl/cuda/plugins.hpp"
+#include "kernels.cuh"
+
+namespace accl {
+namespace cuda {
+
+namespace g {
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 4, ACC_STAGES = 2;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int THREADS = 256;
+constexpr int TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (sm_100 format, version 1)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);      // start address >> 4
+  d |= static_cast<uint64_t>(0) << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                  // stride byte offset: 8 rows x 128 B
+  d |= static_cast<uint64_t>(1) << 46;                          // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                          // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N x M
+__device__ __forceinline__ uint32_t make_idesc(uint32_t m, uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(uint32_t lo_f32, uint32_t hi_f32) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(lo_f32), __uint_as_float(hi_f32));
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+} // namespace g
+
+struct GemmRsParams {
+  DevWorld w;
+  uint64_t out_off;
+  uint32_t m, n, k;
+  uint32_t epoch;
+  uint32_t timeout_us;
+  unsigned int *grid_flags; // zeroed before every launch: [0] zero-phase arrivals, [1] release, [2] finished CTAs, [3] error, [8..] peer offsets
+};
+
+__global__ void __launch_bounds__(g::THREADS, 1)
+k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmRsParams p) {
+  using namespace g;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t *smem_a = smem;
+  uint8_t *smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+  uint64_t *full = bars, *empty = bars + STAGES, *tmem_full = bars + 2 * STAGES, *tmem_empty = bars + 2 * STAGES + ACC_STAGES;
+  uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+  __shared__ uint32_t s_err;
+  __shared__ k::PtrTable s_tab;
+  __shared__ WorkItem s_item; // identity communicator for the sync pads
+  __shared__ uint64_t s_off0[ACCL_MAX_RANKS], s_off2[ACCL_MAX_RANKS];
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t P = p.w.world, me = p.w.rank;
+  const uint32_t tiles_m = p.m / BM, tiles_n = p.n / BN, num_tiles = tiles_m * tiles_n;
+  const uint32_t k_blocks = p.k / BK;
+  const uint32_t rows_per_rank = p.m / P, tiles_m_per_rank = tiles_m / P;
+  char *my_heap = p.w.window + static_cast<uint64_t>(me) * p.w.heap_bytes;
+
+  // ---------------- one-time setup
+  if (threadIdx.x == 0) {
+    s_err = 0;
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4); // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    s_item.comm_size = P;
+    s_item.comm_rank = me;
+    for (uint32_t r = 0; r < static_cast<uint32_t>(ACCL_MAX_RANKS); ++r) s_item.members[r] = static_cast<uint8_t>(r < P ? r : 0);
+    s_item.desc.scenario = 0x47454D4D; // "GEMM": both ends must be in the same plugin
+    s_item.timeout_us = p.timeout_us;
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  // ---------------- zero my output shard (all threads of all CTAs), then meet the peers
+  {
+    dev::Vec16 z{0, 0, 0, 0};
+    char *shard = my_heap + p.out_off;
+    const size_t nvec = static_cast<size_t>(rows_per_rank) * p.n * 2 / 16;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+      dev::st_stream(shard + i * 16, z);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(&p.grid_flags[0], 1u);
+  }
+  if (blockIdx.x == 0 && warp == 3) {
+    // the whole grid has zeroed -> exchange shard offsets with every peer (sync pads, channel MAX_CH-1)
+    if (lane == 0)
+      while (atomicAdd(&p.grid_flags[0], 0u) < gridDim.x) dev::nanosleep(100);
+    __syncwarp();
+    __threadfence();
+  }
+  // (the barrier itself is executed by all threads of CTA 0 below; other CTAs go straight to work)
+  k::Ctx ctx{p.w, s_item, MAX_CH - 1, 1, reinterpret_cast<Ctrl *>(my_heap), &s_err, static_cast<uint64_t>(p.timeout_us) * 1000ull, &s_tab};
+  if (blockIdx.x == 0) {
+    __syncthreads();
+    k::chan_sync(ctx, true, p.out_off, p.out_off, s_off0, s_off2);
+    if (threadIdx.x < P) reinterpret_cast<volatile uint64_t *>(p.grid_flags + 8)[threadIdx.x] = s_off0[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atomicExch(&p.grid_flags[1], 1u); // release the epilogues of every CTA
+    }
+  }
+
+  // ---------------- warp-specialised main loop
+  if (warp == 0) {
+    // ===== TMA producer
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const uint32_t mo = t / tiles_n, nb = t % tiles_n;
+      const uint32_t mb = (mo + (me + 1) * tiles_m_per_rank) % tiles_m; // peers' rows first, mine last
+      for (uint32_t kb = 0; kb < k_blocks; ++kb) {
+        if (lane == 0) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full[stage], static_cast<int>(kb * BK), static_cast<int>(mb * BM));
+          tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full[stage], static_cast<int>(kb * BK), static_cast<int>(nb * BN));
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    const uint32_t idesc = make_idesc(BM, BN);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      if (lane == 0) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1); // epilogue has drained this accumulator
+        tc_fence_after();
+      }
+      __syncwarp();
+      for (uint32_t kb = 0; kb < k_blocks; ++kb) {
+        if (lane == 0) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+          const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
+            umma_f16(tmem_base + acc * BN, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+          umma_commit(&empty[stage]); // smem stage reusable once these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == ACC_STAGES) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> bf16 -> red.add into the owner's shard
+    const uint32_t ew = warp - 4; // == warp % 4: this warp owns TMEM lanes [32*ew, 32*ew+32)
+    if (lane == 0) {
+      uint32_t spins = 0;
+      while (*reinterpret_cast<volatile unsigned int *>(&p.grid_flags[1]) == 0)
+        if (++spins > 64) dev::nanosleep(200);
+    }
+    __syncwarp();
+    __threadfence();
+    const volatile uint64_t *peer_off = reinterpret_cast<const volatile uint64_t *>(p.grid_flags + 8);
+    uint32_t acc = 0, acc_phase = 0;
+    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const uint32_t mo = t / tiles_n, nb = t % tiles_n;
+      const uint32_t mb = (mo + (me + 1) * tiles_m_per_rank) % tiles_m;
+      const uint32_t row = mb * BM + ew * 32 + lane;
+      const uint32_t owner = row / rows_per_rank;
+      char *dst_row = p.w.window + static_cast<uint64_t>(owner) * p.w.heap_bytes + peer_off[owner] +
+                      (static_cast<uint64_t>(row - owner * rows_per_rank) * p.n + static_cast<uint64_t>(nb) * BN) * 2;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((ew * 32u) << 16) + acc * BN + c * 32, r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dev::Vec16 v;
+          v.x = pack_bf16x2(r[8 * j + 0], r[8 * j + 1]);
+          v.y = pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
+          v.z = pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
+          v.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
+          dev::red_add_bf16x8(dst_row + (c * 32 + j * 8) * 2, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == ACC_STAGES) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    __threadfence_system(); // my adds are performed before this CTA reports completion
+  }
+
+  // ---------------- teardown: free TMEM; the last CTA of the grid meets the peers again
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+  __shared__ uint32_t s_last;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(&p.grid_flags[2], 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    // every CTA of this rank has pushed its tiles: when all ranks meet here, every shard is complete
+    k::chan_sync(ctx, false, 0, 0, nullptr, nullptr);
+    if (threadIdx.x == 0 && s_err) atomicOr(&p.grid_flags[3], s_err);
+  }
+}
+
+// ----------------------------------------------------------------------- host
+namespace {
+using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn encode_fn() {
+  static EncodeFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+      throw std::runtime_error("cuTensorMapEncodeTiled unavailable");
+    return reinterpret_cast<EncodeFn>(p);
+  }();
+  return fn;
+}
+
+CUtensorMap make_map(const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {cols, rows};           // innermost first
+  const cuuint64_t strides[1] = {cols * 2};          // bytes between rows
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + cu_error_string(r));
+  return m;
+}
+
+struct PluginState {
+  unsigned int *flags = nullptr; // 64 words
+};
+std::mutex g_state_m;
+std::map<CudaDevice *, PluginState> g_state;
+} // namespace
+
+cudaError_t launch_gemm_rs(CudaDevice &dev, const GemmRsArgs &a, cudaStream_t stream) {
+  using namespace g;
+  const uint32_t P = dev.world().world;
+  if (a.m % (BM * P) || a.n % BN || a.k % BK)
+    throw std::invalid_argument("gemm_rs: need M % (128*world) == 0, N % 256 == 0, K % 64 == 0");
+  ACCL_CUDART(cudaSetDevice(dev.device()));
+  PluginState *st;
+  {
+    std::lock_guard<std::mutex> lk(g_state_m);
+    st = &g_state[&dev];
+    if (!st->flags) {
+      ACCL_CUDART(cudaMalloc(&st->flags, 64 * sizeof(unsigned int)));
+      ACCL_CUDART(cudaMemset(st->flags, 0, 64 * sizeof(unsigned int)));
+    }
+  }
+  cudaFuncSetAttribute(k_plugin_gemm_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  const CUtensorMap ta = make_map(a.a, a.m, a.k, BM, BK);
+  const CUtensorMap tb = make_map(a.w, a.n, a.k, BN, BK);
+  GemmRsParams p;
+  p.w = dev.world();
+  p.out_off = a.out_off;
+  p.m = a.m;
+  p.n = a.n;
+  p.k = a.k;
+  p.epoch = a.epoch;
+  p.timeout_us = dev.timeout_us();
+  p.grid_flags = st->flags;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev.device());
+  const uint32_t tiles = (a.m / BM) * (a.n / BN);
+  const uint32_t grid = std::min<uint32_t>(static_cast<uint32_t>(sms), tiles);
+  ACCL_CUDART(cudaMemsetAsync(st->flags, 0, 64 * sizeof(unsigned int), stream));
+  k_plugin_gemm_rs<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  return cudaGetLastError();
+}
+
+} // namespace cuda
+} // namespace accl

@@ -1,0 +1,79 @@
+"""GPU tests: persistent engine mode, device-issued calls and the fused plugins."""
+import pytest
+import torch
+
+import accl_b200 as A
+from accl_b200 import SUM
+from accl_b200.ops import gemm_reduce_scatter, vadd_allreduce
+
+pytestmark = pytest.mark.gpu
+NGPU = torch.cuda.device_count() if torch.cuda.is_available() else 0
+CFG = dict(n_egr_rx_bufs=4, egr_rx_buf_size=16 << 10, max_egr_size=64 << 10, max_rndzv_size=1 << 30)
+
+
+def devices(world):
+    return [r % max(NGPU, 1) for r in range(world)]
+
+
+def close(a, b, rtol, atol):
+    return torch.allclose(a.cpu().double(), b.cpu().double(), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_gemm_reduce_scatter_matches_fp32_reference(world):
+    M, N, K = 256 * world, 512, 256
+
+    def fn(a, r, w):
+        g = torch.Generator().manual_seed(100 + r)
+        x = (torch.randn(M, K, generator=g) * 0.5).bfloat16().cuda(a.cuda_device)
+        wt = (torch.randn(N, K, generator=g) * 0.5).bfloat16().cuda(a.cuda_device)
+        out = gemm_reduce_scatter(a, x, wt)
+        torch.cuda.current_stream().synchronize()
+        return out.dev.view(M // w, N).float().cpu(), x.float().cpu(), wt.float().cpu()
+
+    res = A.run_cuda_ranks(devices(world), fn, CFG, heap_mb=64, max_ctas=4)
+    full = sum(x @ wt.t() for _, x, wt in res)  # fp32 reference of the same op
+    for r, (shard, _, _) in enumerate(res):
+        ref = full[r * (M // world):(r + 1) * (M // world)]
+        # bf16 output, bf16 adds of `world` partials
+        assert close(shard, ref, 2e-2, 2e-1 * world), (r, (shard - ref).abs().max())
+
+
+def test_engine_mode_collectives():
+    n = 5000
+
+    def fn(a, r, w):
+        s, d = a.create_buffer(n), a.create_buffer(n)
+        s.host[:] = torch.arange(n, dtype=torch.float32) + r
+        for _ in range(3):
+            a.allreduce(s, d, n, SUM)
+        ref = sum(torch.arange(n, dtype=torch.float32) + q for q in range(w))
+        assert torch.equal(d.host, ref)
+        big = 1 << 18
+        bs, bd = a.create_buffer(big), a.create_buffer(big)
+        bs.host[:] = float(r + 1)
+        a.allreduce(bs, bd, big, SUM)
+        assert float(bd.host[-1]) == sum(range(1, w + 1))
+        req = a.nop()
+        assert req.retcode() == 0
+        a.barrier()
+        return a.describe()
+
+    out = A.run_cuda_ranks(devices(2), fn, CFG, heap_mb=64, max_ctas=4, engine=True)
+    assert "mode=engine" in out[0]
+
+
+def test_vadd_plugin_issues_allreduce_from_the_device():
+    n = 1 << 16
+
+    def fn(a, r, w):
+        x, y, out = a.create_buffer(n), a.create_buffer(n), a.create_buffer(n)
+        x.dev.fill_(float(r + 1))
+        y.dev.copy_(torch.arange(n, dtype=torch.float32, device=x.dev.device))
+        status = vadd_allreduce(a, x, y, out)
+        torch.cuda.current_stream().synchronize()
+        assert int(status.item()) == 0
+        ref = torch.arange(n, dtype=torch.float32) * w + sum(range(1, w + 1))
+        assert torch.equal(out.dev.cpu(), ref)
+
+    A.run_cuda_ranks(devices(2), fn, CFG, heap_mb=64, max_ctas=4, engine=True)
