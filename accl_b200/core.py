@@ -376,6 +376,9 @@ def _prepare_cuda_env():
     # ranks sharing one process/GPU need independent hardware queues, or one
     # rank's spinning kernel can block the launch of the peer it waits for
     os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    # Note: with CUDA's lazy module loading the FIRST launch of any kernel may synchronise the
+    # context.  The library preloads its own kernels; if an application keeps the persistent
+    # engine pinned while launching brand-new kernels, export CUDA_MODULE_LOADING=EAGER.
 
 
 def cuda_world(devices, heap_mb=256, multicast=True, max_ctas=8, engine=False, nvls_min_ranks=3, oneshot_kb=512):

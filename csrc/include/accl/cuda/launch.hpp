@@ -17,6 +17,13 @@ struct HostCompletion {
 // one call, one kernel: `item.n_ctas` CTAs cooperate, completion goes to hc (device-visible pinned pointer)
 cudaError_t launch_call(const DevWorld &w, const WorkItem &item, HostCompletion *hc_dev, cudaStream_t stream);
 
+// Force-load every kernel of the library now.  With CUDA's lazy module loading the first
+// launch of a kernel may synchronise the context, which deadlocks against a resident
+// persistent engine (or a peer rank's spinning kernel on the same GPU).
+void preload_engine_kernels();
+void preload_gemm_rs_kernels();
+void preload_vadd_kernels();
+
 // zero the protocol state of my control block (soft reset)
 cudaError_t launch_reset_ctrl(const DevWorld &w, cudaStream_t stream);
 

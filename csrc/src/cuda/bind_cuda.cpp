@@ -41,7 +41,7 @@ void bind_cuda(py::module_ &m) {
     GemmRsArgs g{reinterpret_cast<const void *>(a_ptr), reinterpret_cast<const void *>(w_ptr), out.address(), M, N, K, 0};
     cudaError_t e = launch_gemm_rs(*d, g, reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) throw std::runtime_error(std::string("gemm_reduce_scatter launch: ") + cudaGetErrorString(e));
-  });
+  }, py::call_guard<py::gil_scoped_release>());
   // out = allreduce_sum(x + y): the kernel computes and then issues the collective itself (device API -> engine)
   m.def("vadd_allreduce", [](ACCL &a, BaseBuffer &x, BaseBuffer &y, BaseBuffer &tmp, BaseBuffer &out, uint32_t count,
                              uintptr_t status_dev_ptr, uintptr_t stream) {
@@ -52,7 +52,7 @@ void bind_cuda(py::module_ &m) {
                                           static_cast<uint32_t>(a.get_arithmetic_config_addr({dataType::float32, dataType::float32})),
                                           reinterpret_cast<uint32_t *>(status_dev_ptr), reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) throw std::runtime_error(std::string("vadd_allreduce launch: ") + cudaGetErrorString(e));
-  });
+  }, py::call_guard<py::gil_scoped_release>());
   m.def("cuda_probe", [](int device) { return probe_topology(device).describe(); });
   // N ranks in this process (threads), rank i on devices[i]
   m.def("make_cuda_world", [](std::vector<int> devices, size_t heap_mb, bool multicast, int max_ctas, bool engine,

@@ -192,6 +192,10 @@ CudaDevice::CudaDevice(std::shared_ptr<Oob> oob, const CudaConfig &cfg) : oob_(s
   std::memset(hc_host_, 0, sizeof(HostCompletion) * N_REQ_SLOTS);
   ACCL_CUDART(cudaHostGetDevicePointer(reinterpret_cast<void **>(&hc_dev_), hc_host_, 0));
   slot_owner_.assign(N_REQ_SLOTS, nullptr);
+  preload_engine_kernels();
+  preload_gemm_rs_kernels();
+  preload_vadd_kernels();
+  (void)plugin_counter(); // allocate now: cudaMalloc later could stall behind a running engine kernel
   ACCL_CUDART(launch_reset_ctrl(world_, stream_));
   ACCL_CUDART(cudaStreamSynchronize(stream_));
   oob_->barrier(); // nobody signals a peer whose control block is not zeroed yet

@@ -326,6 +326,15 @@ cudaError_t launch_reset_ctrl(const DevWorld &w, cudaStream_t stream) {
 }
 
 
+void preload_engine_kernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_engine);
+  cudaFuncGetAttributes(&a, k_engine_prepare);
+  cudaFuncGetAttributes(&a, k_call);
+  cudaFuncGetAttributes(&a, k_reset_ctrl);
+  cudaFuncGetAttributes(&a, k_init_comp);
+}
+
 // --------------------------------------------------------------------- host
 struct Engine::Impl {
   HostRing *ring = nullptr, *ring_dev = nullptr;

@@ -387,6 +387,12 @@ std::mutex g_state_m;
 std::map<CudaDevice *, PluginState> g_state;
 } // namespace
 
+void preload_gemm_rs_kernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_plugin_gemm_rs);
+  cudaFuncSetAttribute(k_plugin_gemm_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, g::SMEM_BYTES);
+}
+
 cudaError_t launch_gemm_rs(CudaDevice &dev, const GemmRsArgs &a, cudaStream_t stream) {
   using namespace g;
   const uint32_t P = dev.world().world;
