@@ -1,0 +1,112 @@
+"""GEMM -> reduce-scatter: fused tcgen05 plugin vs cuBLAS + NCCL (BASELINE config #5).
+
+  python bench/gemm_rs.py                       # 1 GPU: fused kernel vs cuBLAS GEMM (tensor-core efficiency)
+  python -m torch.distributed.run --nproc-per-node N ... bench/gemm_rs.py --m 8192 --n 8192 --k 8192
+
+Per rank: A[M, K] and W[N, K] bf16 (its K-slice); result: C = sum_r A_r W_r^T reduce-scattered along M.
+Reports device-timed ms (CUDA events, max over ranks), TFLOP/s per GPU and the fraction of the
+roofline max(FLOPs / measured cuBLAS peak, NVLink bytes / 770 GB/s).
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import accl_b200 as A  # noqa: E402
+from accl_b200.ops import gemm_reduce_scatter  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--m", type=int, default=8192)
+    ap.add_argument("--n", type=int, default=8192)
+    ap.add_argument("--k", type=int, default=8192)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    M, N, K = a.m, a.n, a.k
+    acc = A.cuda_rank(rank, world, local, heap_mb=max(512, (M // world * N * 2 >> 20) * 2 + 256), max_ctas=32)
+    acc.initialize(n_egr_rx_bufs=4, egr_rx_buf_size=16 << 10, max_egr_size=16 << 10, max_rndzv_size=1 << 30)
+    g = torch.Generator(device="cuda").manual_seed(7 + rank)
+    x = (torch.randn(M, K, device="cuda", generator=g) * 0.25).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.25).bfloat16()
+    out = acc.create_buffer(M // world * N, torch.bfloat16)
+    ref_out = torch.empty(M // world, N, dtype=torch.bfloat16, device="cuda")
+
+    def timed(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / iters
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def fused():
+        gemm_reduce_scatter(acc, x, w, out)
+
+    def baseline():
+        c = x @ w.t()
+        if world > 1:
+            dist.reduce_scatter_tensor(ref_out, c)
+        else:
+            ref_out.copy_(c)
+
+    def gemm_only():
+        return x @ w.t()
+
+    ms_f = timed(fused, a.iters)
+    ms_b = timed(baseline, a.iters)
+    ms_g = timed(gemm_only, a.iters)
+    flops = 2.0 * M * N * K
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    nvlink_bytes = M * N * 2 * (world - 1) / world  # partial tiles leaving this GPU
+    t_roof = max(flops / (peak_tf * 1e12), nvlink_bytes / 770e9) * 1e3
+    err = None
+    if a.check:
+        fused()
+        baseline()
+        torch.cuda.synchronize()
+        err = float((out.dev.view(M // world, N).float() - ref_out.float()).abs().max())
+    if rank == 0:
+        row = dict(op="gemm_reduce_scatter", m=M, n=N, k_per_rank=K, world=world, fused_ms=ms_f, cublas_nccl_ms=ms_b,
+                   cublas_gemm_only_ms=ms_g, fused_tflops=flops / ms_f * 1e-9, cublas_tflops=flops / ms_g * 1e-9,
+                   speedup_vs_cublas_nccl=ms_b / ms_f, roofline_ms=t_roof, frac_of_roofline=t_roof / ms_f,
+                   peak_source="MEASURED_PEAKS.json bf16_tflops" if peaks else "fallback 1590", max_abs_err=err)
+        print(json.dumps(row), flush=True)
+        if a.out:
+            os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+            with open(a.out, "a") as fh:
+                fh.write(json.dumps(row) + "\n")
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
