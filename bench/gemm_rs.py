@@ -1,7 +1,7 @@
 """GEMM -> reduce-scatter: fused tcgen05 plugin vs cuBLAS + NCCL (BASELINE config #5).
 
   python bench/gemm_rs.py                       # 1 GPU: fused kernel vs cuBLAS GEMM (tensor-core efficiency)
-  python -m torch.distributed.run --nproc-per-node N ... bench/gemm_rs.py --m 8192 --n 8192 --k 8192
+  python -m torch.distributed.run --nproc-per-node N ... bench/gemm_rs.py --gm 8192 --gn 8192 --gk 8192
 
 Per rank: A[M, K] and W[N, K] bf16 (its K-slice); result: C = sum_r A_r W_r^T reduce-scattered along M.
 Reports device-timed ms (CUDA events, max over ranks), TFLOP/s per GPU and the fraction of the
@@ -22,9 +22,9 @@ from accl_b200.ops import gemm_reduce_scatter  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--m", type=int, default=8192)
-    ap.add_argument("--n", type=int, default=8192)
-    ap.add_argument("--k", type=int, default=8192)
+    ap.add_argument("--gm", dest="m", type=int, default=8192)
+    ap.add_argument("--gn", dest="n", type=int, default=8192)
+    ap.add_argument("--gk", dest="k", type=int, default=8192)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--out", default="")

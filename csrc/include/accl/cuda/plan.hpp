@@ -44,7 +44,7 @@ ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
   }
   if (op == operation::copy || op == operation::combine) {
     w.algo = ALGO_LOCAL;
-    w.n_ctas = plan_ctas(ubytes, 64u << 10, cap);
+    w.n_ctas = plan_ctas(ubytes, 256u << 10, 296); // local: no sync channels involved, fill the chip twice
     return;
   }
   if (op == operation::barrier) {

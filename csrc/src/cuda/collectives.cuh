@@ -248,7 +248,9 @@ enum EgrPattern : uint32_t {
 };
 
 // One generic eager exchange.  Per segment: push what each peer needs from
-// me, wait for what I need from each peer, consume, acknowledge.
+// me, wait for what I need from each peer, consume, acknowledge.  Flag
+// traffic (credits, headers, arrival counters, acks) is handled by one thread
+// per peer in parallel so the latency does not grow with the world size.
 __device__ __noinline__ void egr_collective(const Ctx &c, EgrPattern pat, uint32_t *s_tmp, const char **s_slots) {
   const WorkItem &it = c.it;
   const uint32_t P = c.P(), me = c.r(), root = it.desc.root_src_dst;
@@ -262,43 +264,97 @@ __device__ __noinline__ void egr_collective(const Ctx &c, EgrPattern pat, uint32
   const EgrPlan pl = egr_plan(c, count, wire_t);
   const uint32_t tag = it.desc.tag;
   const size_t se = esize(src_t), de = esize(dst_t);
+  const uint32_t ch = static_cast<uint32_t>(c.cta);
+  __shared__ uint32_t s_v[ACCL_MAX_RANKS];
+  (void)s_tmp;
+  const uint32_t t = threadIdx.x;
+
+  // which peers do I push to / expect from?
+  auto pushes_to = [&](uint32_t q) -> bool {
+    if (q == me) return false;
+    switch (pat) {
+    case EP_ALLREDUCE: case EP_ALLGATHER: case EP_REDUCE_SCATTER: case EP_ALLTOALL: return true;
+    case EP_BCAST: case EP_SCATTER: return me == root;
+    case EP_GATHER: case EP_REDUCE: return q == root;
+    }
+    return false;
+  };
+  auto expects_from = [&](uint32_t q) -> bool {
+    if (q == me) return false;
+    switch (pat) {
+    case EP_ALLREDUCE: case EP_ALLGATHER: case EP_REDUCE_SCATTER: case EP_ALLTOALL: return true;
+    case EP_BCAST: case EP_SCATTER: return me != root && q == root;
+    case EP_GATHER: case EP_REDUCE: return me == root;
+    }
+    return false;
+  };
+  const bool same_src = pat == EP_ALLREDUCE || pat == EP_ALLGATHER || pat == EP_BCAST || pat == EP_GATHER || pat == EP_REDUCE;
 
   for (size_t off = 0; off < pl.part_elems; off += pl.seg) {
     const uint32_t n = static_cast<uint32_t>(pl.part_elems - off < pl.seg ? pl.part_elems - off : pl.seg);
     const size_t e0 = pl.part_off + off; // element offset inside a block
-    if (threadIdx.x < ACCL_MAX_RANKS) s_slots[threadIdx.x] = nullptr;
     __syncthreads();
-    // ---- push phase
-    for (uint32_t k = 1; k < P; ++k) {
-      const uint32_t q = (me + k) % P; // stagger destinations across ranks
-      const char *from = nullptr;
-      switch (pat) {
-      case EP_ALLREDUCE: case EP_ALLGATHER: from = src + e0 * se; break;
-      case EP_REDUCE_SCATTER: case EP_ALLTOALL: from = src + (static_cast<size_t>(q) * count + e0) * se; break;
-      case EP_BCAST: if (me == root) from = src + e0 * se; break;
-      case EP_SCATTER: if (me == root) from = src + (static_cast<size_t>(q) * count + e0) * se; break;
-      case EP_GATHER: case EP_REDUCE: if (q == root) from = src + e0 * se; break;
-      }
-      if (from) egr_push(c, q, from, src_t, wire_t, n, tag, s_tmp);
-    }
-    // ---- wait phase
-    bool ok = true;
-    for (uint32_t k = 1; k < P; ++k) {
-      const uint32_t q = (me + P - k) % P;
-      bool expect = false;
-      switch (pat) {
-      case EP_ALLREDUCE: case EP_ALLGATHER: case EP_REDUCE_SCATTER: case EP_ALLTOALL: expect = true; break;
-      case EP_BCAST: case EP_SCATTER: expect = (me != root && q == root); break;
-      case EP_GATHER: case EP_REDUCE: expect = (me == root); break;
-      }
-      const char *sp = nullptr;
-      if (expect) {
-        sp = egr_wait(c, q, tag, n, wire_t, s_tmp);
-        if (!sp) ok = false;
-      }
-      if (threadIdx.x == 0) s_slots[q] = sp;
+    if (t < ACCL_MAX_RANKS) s_slots[t] = nullptr;
+    // ---- push phase: credits in parallel
+    if (t < P && pushes_to(t)) {
+      const uint32_t peer = c.g(t);
+      const uint32_t v = c.me->egr_sent[ch][peer] + 1;
+      if (v > c.w.egr_depth) wait_ge(&c.me->egr_ack[ch][peer], v - c.w.egr_depth, c, DEQUEUE_BUFFER_TIMEOUT_ERROR);
+      s_v[t] = v;
     }
     __syncthreads();
+    if (same_src && src_t == wire_t && !is_fp8_dt(wire_t)) {
+      // one read of my block, stores fan out to every destination slot
+      int nd = 0;
+      if (t == 0) {
+        for (uint32_t k = 1; k < P; ++k) {
+          const uint32_t q = (me + k) % P;
+          if (pushes_to(q)) c.tab->dst[nd++] = c.heap(c.g(q)) + egr_slot_off(c.w, ch, s_v[q] % c.w.egr_depth, c.w.rank);
+        }
+        c.tab->src[0] = src + e0 * se;
+        *s_tmp = static_cast<uint32_t>(nd);
+      }
+      __syncthreads();
+      nd = static_cast<int>(*s_tmp);
+      if (nd) copy_dispatch(c.tab, nd, static_cast<size_t>(n) * se, 0, 1);
+    } else {
+      for (uint32_t k = 1; k < P; ++k) {
+        const uint32_t q = (me + k) % P; // stagger destinations across ranks
+        if (!pushes_to(q)) continue;
+        const char *from = same_src ? src + e0 * se : src + (static_cast<size_t>(q) * count + e0) * se;
+        char *slot = c.heap(c.g(q)) + egr_slot_off(c.w, ch, s_v[q] % c.w.egr_depth, c.w.rank);
+        cast_copy(slot, wire_t, from, src_t, n, it.ratio_log);
+      }
+    }
+    __syncthreads();
+    if (t < P && pushes_to(t)) { // headers + arrival flags in parallel
+      const uint32_t peer = c.g(t), v = s_v[t];
+      Ctrl *pc = c.ctrl(peer);
+      EgrHdr *h = &pc->egr_hdr[ch][v % c.w.egr_depth][c.w.rank];
+      st_relaxed_sys(&h->tag, tag);
+      st_relaxed_sys(&h->bytes, static_cast<uint32_t>(wire_bytes(wire_t, it.ratio_log, n)));
+      st_relaxed_sys(&h->elems, n);
+      st_relaxed_sys(&h->kind, it.desc.scenario | (wire_t << 8));
+      fence_acq_rel_sys(); // the payload was written by other threads of this CTA (ordered by the barrier above)
+      st_release_sys(&pc->egr_sig[ch][c.w.rank], v);
+      c.me->egr_sent[ch][peer] = v;
+    }
+    // ---- wait phase: one thread per expected peer
+    if (t < P && expects_from(t)) {
+      const uint32_t peer = c.g(t);
+      const uint32_t e = c.me->egr_expect[ch][peer] + 1;
+      if (wait_ge(&c.me->egr_sig[ch][peer], e, c, RECEIVE_TIMEOUT_ERROR)) {
+        const EgrHdr *h = &c.me->egr_hdr[ch][e % c.w.egr_depth][peer];
+        const uint32_t htag = ld_relaxed_sys(&h->tag);
+        if (tag != TAG_ANY && htag != TAG_ANY && htag != tag) atomicOr(c.err, DMA_TAG_MISMATCH_ERROR);
+        if (ld_relaxed_sys(&h->elems) != n) atomicOr(c.err, DMA_NOT_EXPECTED_BTT_ERROR);
+        if ((ld_relaxed_sys(&h->kind) >> 8) != wire_t) atomicOr(c.err, COMPRESSION_ERROR);
+        s_slots[t] = c.heap(c.w.rank) + egr_slot_off(c.w, ch, e % c.w.egr_depth, peer);
+      }
+      c.me->egr_expect[ch][peer] = e;
+    }
+    __syncthreads();
+    bool ok = *c.err == 0;
     // ---- consume phase
     if (ok) {
       switch (pat) {
@@ -324,19 +380,19 @@ __device__ __noinline__ void egr_collective(const Ctx &c, EgrPattern pat, uint32
           }
         break;
       case EP_BCAST:
-        if (me != root) cast_copy(dst + e0 * se, src_t, s_slots[root], wire_t, n, it.ratio_log);
+        if (me != root && s_slots[root]) cast_copy(dst + e0 * se, src_t, s_slots[root], wire_t, n, it.ratio_log);
         break;
       case EP_SCATTER:
         if (me == root) cast_copy(dst + e0 * de, dst_t, src + (static_cast<size_t>(me) * count + e0) * se, src_t, n, it.ratio_log);
-        else cast_copy(dst + e0 * de, dst_t, s_slots[root], wire_t, n, it.ratio_log);
+        else if (s_slots[root]) cast_copy(dst + e0 * de, dst_t, s_slots[root], wire_t, n, it.ratio_log);
         break;
       }
     }
-    // ---- credits
-    for (uint32_t q = 0; q < P; ++q)
-      if (q != me && s_slots[q]) egr_ack(c, q);
+    // ---- credits back to the senders
     __syncthreads();
+    if (t < P && s_slots[t]) st_relaxed_sys(&c.ctrl(c.g(t))->egr_ack[ch][c.w.rank], c.me->egr_expect[ch][c.g(t)]);
   }
+  __syncthreads();
 }
 
 // eager point-to-point (channel 0 only)

@@ -361,12 +361,12 @@ __device__ __forceinline__ void copy_simple(char *dst, const char *src, size_t b
   if (aligned) {
     const size_t nvec = bytes / 16;
     size_t i = tid;
-    for (; i + 3 * stride < nvec; i += 4 * stride) {
-      Vec16 v[4];
+    for (; i + 7 * stride < nvec; i += 8 * stride) {
+      Vec16 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ld_relaxed_sys16(src + (i + u * stride) * 16);
+      for (int u = 0; u < 8; ++u) v[u] = ld_relaxed_sys16(src + (i + u * stride) * 16);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) st_relaxed_sys16(dst + (i + u * stride) * 16, v[u]);
+      for (int u = 0; u < 8; ++u) st_relaxed_sys16(dst + (i + u * stride) * 16, v[u]);
     }
     for (; i < nvec; i += stride) st_relaxed_sys16(dst + i * 16, ld_relaxed_sys16(src + i * 16));
     done = nvec * 16;

@@ -15,10 +15,13 @@
 //               finished accumulators
 //   warp 2      allocates / frees TMEM
 //   warps 4-7   epilogue: tcgen05.ld the fp32 accumulator (32 lanes x 32
-//               columns per instruction), convert to bf16 and emit it with
-//               red.global.add.noftz.v4.bf16x2 directly into the OWNER rank's
-//               output shard through the peer-mapped symmetric heap — the tile
-//               goes into the collective as it leaves the tensor core
+//               columns per instruction), convert to bf16, stage 32x64 boxes in
+//               128B-swizzled smem and hand them to the TMA unit as
+//               cp.reduce.async.bulk.tensor ... .add (SASS UTMAREDG.2D.ADD) whose
+//               tensor map points at the OWNER rank's output shard in the
+//               peer-mapped symmetric heap — the tile goes into the collective
+//               as it leaves the tensor core, coalesced by hardware, with no
+//               SM store instructions on the NVLink path
 // Tiles are visited owner-rotated (peers' rows first, own rows last) so the
 // NVLink traffic overlaps the remaining math.  Shards are zeroed in-kernel and
 // two flag barriers over the sync pads (channel MAX_CH-1) bracket the adds.
@@ -29,6 +32,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstring>
 #include <map>
 #include <mutex>
 
@@ -47,7 +51,10 @@ constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_COLS = 64;                        // columns per TMA reduce box (128 B of bf16: one swizzle row)
+constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;    // 32 rows x 64 cols bf16 = 4 KB
+constexpr int EPI_BYTES = 4 /*warps*/ * 2 /*double buffer*/ * EPI_BUF_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int THREADS = 256;
 constexpr int TMEM_COLS = 512;
 
@@ -131,11 +138,24 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// smem tile -> global memory of the tensor map's rank, element-wise ADD performed by the TMA unit
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, const void *smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(uint32_t lo_f32, uint32_t hi_f32) {
   __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(lo_f32), __uint_as_float(hi_f32));
   return *reinterpret_cast<uint32_t *>(&v);
 }
 } // namespace g
+
+struct alignas(64) OutMaps {
+  CUtensorMap m[ACCL_MAX_RANKS]; // owner rank o: its [M/P, N] bf16 shard through my peer mapping
+};
 
 struct GemmRsParams {
   DevWorld w;
@@ -147,13 +167,15 @@ struct GemmRsParams {
 };
 
 __global__ void __launch_bounds__(g::THREADS, 1)
-k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmRsParams p) {
+k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ OutMaps out_maps, GemmRsParams p) {
   using namespace g;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t *smem_a = smem;
   uint8_t *smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+  uint8_t *smem_epi = smem + STAGES * STAGE_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
   uint64_t *full = bars, *empty = bars + STAGES, *tmem_full = bars + 2 * STAGES, *tmem_empty = bars + 2 * STAGES + ACC_STAGES;
   uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2 * ACC_STAGES);
 
@@ -296,30 +318,45 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     __syncwarp();
     __threadfence();
-    const volatile uint64_t *peer_off = reinterpret_cast<const volatile uint64_t *>(p.grid_flags + 8);
-    uint32_t acc = 0, acc_phase = 0;
+    // shards must sit at the same heap offset on every rank (the output tensor maps assume it)
+    if (lane < P && reinterpret_cast<const volatile uint64_t *>(p.grid_flags + 8)[lane] != p.out_off) atomicOr(&p.grid_flags[3], static_cast<unsigned>(DMA_MISMATCH_ERROR));
+    uint8_t *my_epi = smem_epi + ew * 2 * EPI_BUF_BYTES;
+    uint32_t acc = 0, acc_phase = 0, ebuf = 0;
     for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const uint32_t mo = t / tiles_n, nb = t % tiles_n;
       const uint32_t mb = (mo + (me + 1) * tiles_m_per_rank) % tiles_m;
-      const uint32_t row = mb * BM + ew * 32 + lane;
-      const uint32_t owner = row / rows_per_rank;
-      char *dst_row = p.w.window + static_cast<uint64_t>(owner) * p.w.heap_bytes + peer_off[owner] +
-                      (static_cast<uint64_t>(row - owner * rows_per_rank) * p.n + static_cast<uint64_t>(nb) * BN) * 2;
+      const uint32_t row0 = mb * BM + ew * 32;     // first of this warp's 32 rows
+      const uint32_t owner = row0 / rows_per_rank; // a warp's rows never straddle owners
+      const int local_row0 = static_cast<int>(row0 - owner * rows_per_rank);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < BN / EPI_COLS; ++c) {
+        uint8_t *buf = my_epi + ebuf * EPI_BUF_BYTES;
+        // the TMA unit must be done READING this buffer (issued two chunks ago)
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((ew * 32u) << 16) + acc * BN + c * 32, r);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          dev::Vec16 v;
-          v.x = pack_bf16x2(r[8 * j + 0], r[8 * j + 1]);
-          v.y = pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
-          v.z = pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
-          v.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
-          dev::red_add_bf16x8(dst_row + (c * 32 + j * 8) * 2, v);
+        for (int h = 0; h < 2; ++h) {
+          tmem_ld_32x32(tmem_base + ((ew * 32u) << 16) + acc * BN + c * EPI_COLS + h * 32, r);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // 16-byte chunk index inside the 128-byte row, XOR-swizzled with the row (SWIZZLE_128B)
+            const uint32_t chunk = static_cast<uint32_t>(h * 4 + j) ^ (lane & 7u);
+            uint4 v;
+            v.x = pack_bf16x2(r[8 * j + 0], r[8 * j + 1]);
+            v.y = pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
+            v.z = pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
+            v.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
+            *reinterpret_cast<uint4 *>(buf + lane * 128 + chunk * 16) = v;
+          }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the TMA unit
+        __syncwarp();
+        if (lane == 0)
+          tma_reduce_add_2d(&out_maps.m[owner], buf, static_cast<int>(nb * BN + c * EPI_COLS), local_row0);
+        ebuf ^= 1;
       }
       tc_fence_before();
       __syncwarp();
@@ -329,6 +366,8 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         acc_phase ^= 1;
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // all my reductions have completed
+    __syncwarp();
     __threadfence_system(); // my adds are performed before this CTA reports completion
   }
 
@@ -411,6 +450,11 @@ cudaError_t launch_gemm_rs(CudaDevice &dev, const GemmRsArgs &a, cudaStream_t st
   cudaFuncSetAttribute(k_plugin_gemm_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   const CUtensorMap ta = make_map(a.a, a.m, a.k, BM, BK);
   const CUtensorMap tb = make_map(a.w, a.n, a.k, BN, BK);
+  OutMaps om;
+  std::memset(&om, 0, sizeof(om));
+  for (uint32_t o = 0; o < P; ++o) // symmetric allocation: the shard sits at out_off in every heap (verified in-kernel)
+    om.m[o] = make_map(dev.world().window + static_cast<uint64_t>(o) * dev.world().heap_bytes + a.out_off, a.m / P, a.n, 32,
+                       EPI_COLS);
   GemmRsParams p;
   p.w = dev.world();
   p.out_off = a.out_off;
@@ -425,7 +469,7 @@ cudaError_t launch_gemm_rs(CudaDevice &dev, const GemmRsArgs &a, cudaStream_t st
   const uint32_t tiles = (a.m / BM) * (a.n / BN);
   const uint32_t grid = std::min<uint32_t>(static_cast<uint32_t>(sms), tiles);
   ACCL_CUDART(cudaMemsetAsync(st->flags, 0, 64 * sizeof(unsigned int), stream));
-  k_plugin_gemm_rs<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  k_plugin_gemm_rs<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, om, p);
   return cudaGetLastError();
 }
 
