@@ -381,16 +381,17 @@ def _prepare_cuda_env():
     # engine pinned while launching brand-new kernels, export CUDA_MODULE_LOADING=EAGER.
 
 
-def cuda_world(devices, heap_mb=256, multicast=True, max_ctas=8, engine=False, nvls_min_ranks=3, oneshot_kb=512):
+def cuda_world(devices, heap_mb=256, multicast=True, max_ctas=8, engine=False, nvls_min_ranks=3, oneshot_kb=512,
+               nvls_ops=-1):
     """In-process world on real GPUs: rank i drives devices[i] (a device may
     appear several times: ranks then share that GPU, without NVLS)."""
     _prepare_cuda_env()
-    impls = _C.make_cuda_world(list(devices), heap_mb, multicast, max_ctas, engine, nvls_min_ranks, oneshot_kb)
+    impls = _C.make_cuda_world(list(devices), heap_mb, multicast, max_ctas, engine, nvls_min_ranks, oneshot_kb, nvls_ops)
     return [Accl(a, r, len(devices), cuda_device=devices[r]) for r, a in enumerate(impls)]
 
 
 def cuda_rank(rank=None, world_size=None, device=None, addr=None, port=None, heap_mb=1024, multicast=True,
-              max_ctas=32, engine=False, nvls_min_ranks=3, oneshot_kb=512):
+              max_ctas=32, engine=False, nvls_min_ranks=3, oneshot_kb=512, nvls_ops=-1):
     """One rank per process (torchrun): RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT."""
     _prepare_cuda_env()
     rank = int(os.environ.get("RANK", 0)) if rank is None else rank
@@ -402,7 +403,7 @@ def cuda_rank(rank=None, world_size=None, device=None, addr=None, port=None, hea
     if port is None:
         port = int(os.environ.get("ACCL_PORT", int(os.environ.get("MASTER_PORT", 29500)) + 137))
     impl = _C.make_cuda_rank(rank, world_size, device, addr, port, heap_mb, multicast, max_ctas, engine,
-                             nvls_min_ranks, oneshot_kb)
+                             nvls_min_ranks, oneshot_kb, nvls_ops)
     return Accl(impl, rank, world_size, cuda_device=device)
 
 

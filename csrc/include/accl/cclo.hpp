@@ -103,6 +103,14 @@ public:
   // GPU backends: stream on which subsequent calls and buffer syncs are enqueued
   virtual void set_stream(void *stream) { (void)stream; }
 
+  // Optional fast path for blocking calls whose operands live on the host: overlap the
+  // host->device staging, the collective and the device->host read-back chunk by chunk.
+  // Returns nullptr when the backend (or this call) does not support it.
+  virtual ACCLRequest *call_host_pipelined(const Options &options) {
+    (void)options;
+    return nullptr;
+  }
+
   // backend-owned memory
   virtual std::shared_ptr<BufferStorage> allocate(size_t bytes, bufferKind kind) = 0;
   // wrap caller-owned host memory (mirror is the caller's array)

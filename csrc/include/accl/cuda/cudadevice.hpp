@@ -36,7 +36,9 @@ struct CudaConfig {
   bool multicast = true;       // try to set up NVLS
   int max_ctas = 32;           // CTAs a single call may use (== sync channels used)
   int nvls_min_ranks = 3;      // below this, peer loads/stores beat the switch round trip
+  size_t host_pipeline_chunk = 16u << 20; // chunk size of the pipelined host-operand path (0 = off)
   size_t oneshot_max_bytes = 512 << 10; // allreduce: pull-everything one-shot up to this size
+  uint32_t nvls_ops = NVLS_OPS_DEFAULT;  // which operations may use multimem (bit = operation code)
   bool engine = false;         // route calls through the persistent engine kernel
   int engine_idle_us = 200;    // engine kernel parks itself after this idle time (0 = never)
 };
@@ -47,7 +49,7 @@ struct CudaRequest : public BaseRequest {
   using BaseRequest::BaseRequest;
   ~CudaRequest() override;
   CudaDevice *dev = nullptr;
-  cudaEvent_t done = nullptr;
+  cudaStream_t stream = nullptr; // stream the call was enqueued on (fallback for long waits)
   uint32_t slot = 0, seq = 0;
   bool immediate = false; // completed on the host (config calls)
   std::vector<std::shared_ptr<BufferStorage>> temps; // staging buffers that live as long as the call
@@ -65,6 +67,7 @@ public:
 
   ACCLRequest *call(const Options &options) override;
   ACCLRequest *start(const Options &options) override;
+  ACCLRequest *call_host_pipelined(const Options &options) override;
   val_t read(addr_t offset) override;
   void write(addr_t offset, val_t val) override;
   void wait(ACCLRequest *request) override;
@@ -112,6 +115,7 @@ private:
   DevWorld world_{};
   cudaStream_t stream_ = nullptr;
   cudaStream_t op_stream_ = nullptr;
+  cudaStream_t h2d_stream_ = nullptr, d2h_stream_ = nullptr;
   std::vector<uint32_t> shadow_; // host copy of exchange memory
   HostCompletion *hc_host_ = nullptr, *hc_dev_ = nullptr;
   std::vector<std::shared_ptr<CudaRequest>> slot_owner_;

@@ -8,10 +8,12 @@ namespace accl {
 namespace cuda {
 
 // host-visible mirror of a finished call (pinned, written by the last CTA)
-struct HostCompletion {
+// One 16-byte record, written by the device with a single vector store (one PCIe write): no
+// system-scope fence on the kernel's critical path.
+struct alignas(16) HostCompletion {
+  volatile uint32_t seq;      // request sequence the record belongs to
   volatile uint32_t retcode;
-  volatile uint32_t seq;
-  volatile unsigned long long t_start, t_end;
+  volatile unsigned long long duration_ns; // %globaltimer: last CTA out - first CTA in
 };
 
 // one call, one kernel: `item.n_ctas` CTAs cooperate, completion goes to hc (device-visible pinned pointer)

@@ -22,7 +22,15 @@ struct PlanCfg {
   uint32_t has_mc;
   uint32_t heap_world;
   uint64_t oneshot_max_bytes;
+  // bit i set: operation code i may use the in-switch (multimem) algorithm.  Default: allreduce,
+  // bcast and reduce.  Measured on 4 x B200 (profiles/sweep_4gpu_*.csv): allgather and
+  // reduce_scatter move less data per link with peer stores / loads than through the switch.
+  uint32_t nvls_ops;
+  uint32_t pad;
 };
+constexpr uint32_t NVLS_OPS_DEFAULT = (1u << static_cast<uint32_t>(operation::allreduce)) |
+                                      (1u << static_cast<uint32_t>(operation::bcast)) |
+                                      (1u << static_cast<uint32_t>(operation::reduce));
 
 ACCL_HD uint32_t plan_ctas(uint64_t bytes, uint64_t per_cta, uint32_t cap) {
   uint64_t n = (bytes + per_cta - 1) / per_cta;
@@ -64,7 +72,8 @@ ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
     w.n_ctas = (op == operation::send || op == operation::recv) ? 1 : plan_ctas(ubytes, 16u << 10, ecap);
     return;
   }
-  const bool nvls = cfg.has_mc && P >= cfg.nvls_min_ranks && P == cfg.heap_world;
+  const bool nvls = cfg.has_mc && P >= cfg.nvls_min_ranks && P == cfg.heap_world &&
+                    ((cfg.nvls_ops >> static_cast<uint32_t>(op)) & 1u);
   w.algo = nvls ? ALGO_NVLS : ALGO_P2P;
   if (op == operation::allreduce && ubytes <= cfg.oneshot_max_bytes) w.algo = ALGO_P2P_ONESHOT;
   if (op == operation::send || op == operation::recv) w.algo = ALGO_P2P;

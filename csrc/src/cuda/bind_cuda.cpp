@@ -14,7 +14,7 @@ namespace accl {
 namespace cuda {
 
 static CudaConfig make_cfg(int device, size_t heap_mb, bool multicast, int max_ctas, bool engine, int nvls_min_ranks,
-                           size_t oneshot_kb) {
+                           size_t oneshot_kb, int nvls_ops = -1) {
   CudaConfig c;
   c.device = device;
   c.heap_bytes = heap_mb << 20;
@@ -23,6 +23,7 @@ static CudaConfig make_cfg(int device, size_t heap_mb, bool multicast, int max_c
   c.engine = engine;
   c.nvls_min_ranks = nvls_min_ranks;
   c.oneshot_max_bytes = oneshot_kb << 10;
+  if (nvls_ops >= 0) c.nvls_ops = static_cast<uint32_t>(nvls_ops);
   return c;
 }
 
@@ -56,24 +57,25 @@ void bind_cuda(py::module_ &m) {
   m.def("cuda_probe", [](int device) { return probe_topology(device).describe(); });
   // N ranks in this process (threads), rank i on devices[i]
   m.def("make_cuda_world", [](std::vector<int> devices, size_t heap_mb, bool multicast, int max_ctas, bool engine,
-                              int nvls_min_ranks, size_t oneshot_kb) {
+                              int nvls_min_ranks, size_t oneshot_kb, int nvls_ops) {
     std::vector<std::unique_ptr<ACCL>> out;
-    auto devs = make_local_world(devices, make_cfg(0, heap_mb, multicast, max_ctas, engine, nvls_min_ranks, oneshot_kb));
+    auto devs = make_local_world(devices, make_cfg(0, heap_mb, multicast, max_ctas, engine, nvls_min_ranks, oneshot_kb, nvls_ops));
     for (auto &d : devs) out.emplace_back(new ACCL(std::move(d)));
     return out;
   }, py::arg("devices"), py::arg("heap_mb") = 256, py::arg("multicast") = true, py::arg("max_ctas") = 32,
-        py::arg("engine") = false, py::arg("nvls_min_ranks") = 3, py::arg("oneshot_kb") = 512,
+        py::arg("engine") = false, py::arg("nvls_min_ranks") = 3, py::arg("oneshot_kb") = 512, py::arg("nvls_ops") = -1,
         py::call_guard<py::gil_scoped_release>());
   // one rank per process; bootstrap over a private TCP rendezvous on addr:port
   m.def("make_cuda_rank", [](int rank, int world, int device, const std::string &addr, int port, size_t heap_mb,
-                             bool multicast, int max_ctas, bool engine, int nvls_min_ranks, size_t oneshot_kb) {
+                             bool multicast, int max_ctas, bool engine, int nvls_min_ranks, size_t oneshot_kb, int nvls_ops) {
     auto oob = std::make_shared<TcpOob>(rank, world, addr, port);
     auto dev = std::unique_ptr<CCLO>(
-        new CudaDevice(oob, make_cfg(device, heap_mb, multicast, max_ctas, engine, nvls_min_ranks, oneshot_kb)));
+        new CudaDevice(oob, make_cfg(device, heap_mb, multicast, max_ctas, engine, nvls_min_ranks, oneshot_kb, nvls_ops)));
     return std::unique_ptr<ACCL>(new ACCL(std::move(dev)));
   }, py::arg("rank"), py::arg("world_size"), py::arg("device"), py::arg("addr") = "127.0.0.1", py::arg("port") = 29637,
         py::arg("heap_mb") = 1024, py::arg("multicast") = true, py::arg("max_ctas") = 32, py::arg("engine") = false,
-        py::arg("nvls_min_ranks") = 3, py::arg("oneshot_kb") = 512, py::call_guard<py::gil_scoped_release>());
+        py::arg("nvls_min_ranks") = 3, py::arg("oneshot_kb") = 512, py::arg("nvls_ops") = -1,
+        py::call_guard<py::gil_scoped_release>());
 }
 
 } // namespace cuda

@@ -1,6 +1,7 @@
 #include "accl/cuda/cudadevice.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <map>
 #include <sstream>
@@ -115,15 +116,13 @@ private:
 } // namespace
 
 // ------------------------------------------------------------------ request
-CudaRequest::~CudaRequest() {
-  if (done) cudaEventDestroy(done);
-}
+CudaRequest::~CudaRequest() {}
 
 void CudaRequest::finish() {
   if (status() == operationStatus::COMPLETED) return;
   HostCompletion *hc = &dev->hc_host_[slot];
   const uint32_t rc = hc->seq == seq ? hc->retcode : static_cast<uint32_t>(DMA_INTERNAL_ERROR);
-  const uint64_t dur = hc->t_end > hc->t_start ? hc->t_end - hc->t_start : 0;
+  const uint64_t dur = hc->duration_ns;
   for (auto &co : copy_out) { // results of host-resident operands
     co.second->from_device(0, co.second->bytes());
     if (co.first && co.first->byte_array()) std::memcpy(co.first->byte_array(), co.second->host_ptr(), co.first->size());
@@ -133,15 +132,31 @@ void CudaRequest::finish() {
   complete(rc, dur);
 }
 
+// Completion is detected on the pinned HostCompletion record the kernel writes last
+// (retcode, timestamps, then seq after a system fence): no CUDA event per call.
+static inline bool hc_done(const HostCompletion *hc, uint32_t seq) { return hc->seq == seq; }
+
 void CudaRequest::wait() {
   if (status() == operationStatus::COMPLETED) return;
   if (!immediate) {
-    cudaSetDevice(dev->device());
-    cudaError_t e = cudaEventSynchronize(done);
-    if (e != cudaSuccess) {
-      complete(DMA_INTERNAL_ERROR, 0);
-      throw std::runtime_error(std::string("CUDA error while waiting for a call: ") + cudaGetErrorString(e));
+    const HostCompletion *hc = &dev->hc_host_[slot];
+    // short spin for latency, then let the driver block on the stream
+    const auto t0 = std::chrono::steady_clock::now();
+    while (!hc_done(hc, seq)) {
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) {
+        cudaSetDevice(dev->device());
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) {
+          complete(DMA_INTERNAL_ERROR, 0);
+          throw std::runtime_error(std::string("CUDA error while waiting for a call: ") + cudaGetErrorString(e));
+        }
+        // the stream has drained: the record must be there (engine mode: the stream waited for it)
+        const auto t1 = std::chrono::steady_clock::now();
+        while (!hc_done(hc, seq) && std::chrono::steady_clock::now() - t1 < std::chrono::seconds(2)) std::this_thread::yield();
+        break;
+      }
     }
+    std::atomic_thread_fence(std::memory_order_acquire);
   }
   finish();
 }
@@ -150,7 +165,7 @@ bool CudaRequest::wait(std::chrono::milliseconds timeout) {
   auto deadline = std::chrono::steady_clock::now() + timeout;
   while (!test()) {
     if (std::chrono::steady_clock::now() > deadline) return false;
-    std::this_thread::sleep_for(std::chrono::microseconds(50));
+    std::this_thread::sleep_for(std::chrono::microseconds(20));
   }
   return true;
 }
@@ -158,11 +173,8 @@ bool CudaRequest::wait(std::chrono::milliseconds timeout) {
 bool CudaRequest::test() {
   if (status() == operationStatus::COMPLETED) return true;
   if (!immediate) {
-    cudaSetDevice(dev->device());
-    if (cudaEventQuery(done) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return false;
-    }
+    if (!hc_done(&dev->hc_host_[slot], seq)) return false;
+    std::atomic_thread_fence(std::memory_order_acquire);
   }
   finish();
   return true;
@@ -210,6 +222,8 @@ CudaDevice::~CudaDevice() {
   slot_owner_.clear();
   if (hc_host_) cudaFreeHost(hc_host_);
   heap_.reset();
+  if (h2d_stream_) cudaStreamDestroy(h2d_stream_);
+  if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -363,6 +377,8 @@ PlanCfg CudaDevice::plan_cfg() const {
   c.has_mc = heap_->has_multicast() ? 1u : 0u;
   c.heap_world = static_cast<uint32_t>(heap_->world());
   c.oneshot_max_bytes = cfg_.oneshot_max_bytes;
+  c.nvls_ops = cfg_.nvls_ops;
+  c.pad = 0;
   return c;
 }
 
@@ -432,12 +448,76 @@ ACCLRequest *CudaDevice::start(const Options &options) {
   if (next_seq_ == 0) next_seq_ = 1;
   w.req_slot = slot;
   w.req_seq = req->seq;
-  ACCL_CUDART(cudaEventCreateWithFlags(&req->done, cudaEventDisableTiming));
+  req->stream = s;
   if (engine_) engine_->submit(w, &hc_dev_[slot], s);
   else ACCL_CUDART(launch_call(world_, w, &hc_dev_[slot], s));
-  ACCL_CUDART(cudaEventRecord(req->done, s));
   req->set_status(operationStatus::EXECUTING);
   return h;
+}
+
+// Blocking all-reduce on host-resident operands, software-pipelined: chunk i is copied in on
+// the H2D engine while chunk i-1 is being reduced over NVLink and chunk i-2 is copied out on
+// the D2H engine (PCIe is full duplex).  Same chunking on every rank by construction.
+ACCLRequest *CudaDevice::call_host_pipelined(const Options &options) {
+  if (options.scenario != operation::allreduce || cfg_.host_pipeline_chunk == 0) return nullptr;
+  BaseBuffer *src = options.addr_0, *dst = options.addr_2;
+  if (!src || !dst || src->is_dummy() || dst->is_dummy() || src->is_host_only() || dst->is_host_only()) return nullptr;
+  if (options.compression_flags != compressionFlags::NO_COMPRESSION || !src->byte_array() || !dst->byte_array()) return nullptr;
+  const size_t es = dtype_bytes(src->type());
+  const size_t total = options.count;
+  size_t chunk = cfg_.host_pipeline_chunk / es;
+  if (total * es < 2 * cfg_.host_pipeline_chunk) return nullptr; // too small to be worth pipelining
+  ACCL_CUDART(cudaSetDevice(cfg_.device));
+  if (!h2d_stream_) {
+    ACCL_CUDART(cudaStreamCreateWithFlags(&h2d_stream_, cudaStreamNonBlocking));
+    ACCL_CUDART(cudaStreamCreateWithFlags(&d2h_stream_, cudaStreamNonBlocking));
+  }
+  cudaStream_t main = options.stream ? static_cast<cudaStream_t>(options.stream) : op_stream();
+  const size_t nchunks = (total + chunk - 1) / chunk;
+  std::vector<cudaEvent_t> ev_in(nchunks), ev_out(nchunks);
+  std::vector<ACCLRequest *> reqs;
+  cudaEvent_t ev_start;
+  ACCL_CUDART(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+  ACCL_CUDART(cudaEventRecord(ev_start, main)); // staging starts after whatever the caller queued before
+  ACCL_CUDART(cudaStreamWaitEvent(h2d_stream_, ev_start, 0));
+  uint32_t rc = 0;
+  uint64_t dur = 0;
+  for (size_t c = 0; c < nchunks; ++c) {
+    const size_t e0 = c * chunk, n = std::min(chunk, total - e0);
+    auto s = src->slice(e0, e0 + n);
+    auto d = dst->slice(e0, e0 + n);
+    ACCL_CUDART(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+    ACCL_CUDART(cudaEventCreateWithFlags(&ev_out[c], cudaEventDisableTiming));
+    ACCL_CUDART(cudaMemcpyAsync(s->device_ptr(), s->byte_array(), n * es, cudaMemcpyHostToDevice, h2d_stream_));
+    ACCL_CUDART(cudaEventRecord(ev_in[c], h2d_stream_));
+    ACCL_CUDART(cudaStreamWaitEvent(main, ev_in[c], 0));
+    Options o = options;
+    o.addr_0 = s.get();
+    o.addr_2 = d.get();
+    o.count = static_cast<unsigned int>(n);
+    o.stream = main;
+    reqs.push_back(start(o));
+    ACCL_CUDART(cudaEventRecord(ev_out[c], main));
+    ACCL_CUDART(cudaStreamWaitEvent(d2h_stream_, ev_out[c], 0));
+    ACCL_CUDART(cudaMemcpyAsync(d->byte_array(), d->device_ptr(), n * es, cudaMemcpyDeviceToHost, d2h_stream_));
+  }
+  ACCL_CUDART(cudaStreamSynchronize(d2h_stream_));
+  for (ACCLRequest *r : reqs) {
+    wait(r);
+    rc |= get_retcode(r);
+    dur += get_duration(r);
+    free_request(r);
+  }
+  for (size_t c = 0; c < nchunks; ++c) {
+    cudaEventDestroy(ev_in[c]);
+    cudaEventDestroy(ev_out[c]);
+  }
+  cudaEventDestroy(ev_start);
+  auto req = std::make_shared<CudaRequest>(options);
+  req->dev = this;
+  req->immediate = true;
+  req->complete(rc, dur);
+  return requests_.add(req);
 }
 
 ACCLRequest *CudaDevice::call(const Options &options) {
@@ -469,10 +549,6 @@ void CudaDevice::free_request(ACCLRequest *request) {
       // still in flight: keep the slot owner alive, drop only the user handle
     } else {
       if (slot_owner_[r->slot] == r) slot_owner_[r->slot] = nullptr;
-      if (r->done) {
-        cudaEventDestroy(r->done);
-        r->done = nullptr;
-      }
     }
   }
   requests_.erase(request);

@@ -44,6 +44,12 @@
 namespace accl {
 namespace cuda {
 
+__device__ __forceinline__ void publish_completion(HostCompletion *hc, uint32_t seq, uint32_t rc, unsigned long long dur) {
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(hc), "r"(seq), "r"(rc), "r"(static_cast<uint32_t>(dur)),
+               "r"(static_cast<uint32_t>(dur >> 32))
+               : "memory");
+}
+
 enum EngineState : uint32_t { ENG_STOPPED = 0, ENG_RUNNING = 1, ENG_EXITING = 2 };
 
 struct HostRingSlot {
@@ -117,25 +123,19 @@ __device__ void engine_worker(const DevWorld &w, int nworkers) {
         if (atomicAdd(&cp->done_ctas, 1u) == static_cast<uint32_t>(nctas) - 1) {
           __threadfence();
           const uint32_t rc = cp->retcode;
-          if (s_item.hc_ptr) {
-            HostCompletion *hc = reinterpret_cast<HostCompletion *>(s_item.hc_ptr);
-            hc->retcode = rc;
-            hc->t_start = cp->t_start;
-            hc->t_end = cp->t_end;
-            __threadfence_system();
-            hc->seq = s_item.req_seq;
-          }
+          const unsigned long long dur = cp->t_end - cp->t_start;
           me->exch[exchmem::RETCODE / 4] = rc;
-          me->exch[exchmem::PERFCNT_LO / 4] = static_cast<uint32_t>(cp->t_end - cp->t_start);
-          if (s_item.dev_ticket)
-            dev::st_release_sys(&me->dev_status[(s_item.dev_ticket - 1) % RING_SLOTS],
-                                s_item.dev_ticket | (static_cast<unsigned long long>(rc) << 32));
-          if (s_item.host_seq) dev::st_release_sys(&me->host_done, s_item.host_seq);
+          me->exch[exchmem::PERFCNT_LO / 4] = static_cast<uint32_t>(dur);
           cp->retcode = 0;
           cp->done_ctas = 0;
           cp->t_start = ~0ull;
           cp->t_end = 0;
-          __threadfence_system();
+          __threadfence();
+          if (s_item.dev_ticket)
+            dev::st_release_sys(&me->dev_status[(s_item.dev_ticket - 1) % RING_SLOTS],
+                                s_item.dev_ticket | (static_cast<unsigned long long>(rc) << 32));
+          if (s_item.host_seq) dev::st_release_sys(&me->host_done, s_item.host_seq);
+          if (s_item.hc_ptr) publish_completion(reinterpret_cast<HostCompletion *>(s_item.hc_ptr), s_item.req_seq, rc, dur);
           // in-order retirement: the control CTA and stream waits key off this counter
           dev::st_release_sys(&me->done_count, next + 1);
         }
@@ -277,24 +277,27 @@ __global__ void __launch_bounds__(k::BLOCK) k_call(DevWorld w, WorkItem it, Host
   k::run_work(w, it, blockIdx.x, gridDim.x, &s_err);
   __syncthreads();
   if (threadIdx.x == 0) {
-    Ctrl *me = reinterpret_cast<Ctrl *>(w.window + static_cast<uint64_t>(w.rank) * w.heap_bytes);
-    Completion *cp = &me->comp[it.req_slot];
-    if (s_err) atomicOr(&cp->retcode, s_err);
-    atomicMin(&cp->t_start, t0);
-    atomicMax(&cp->t_end, dev::globaltimer_ns());
-    __threadfence();
-    if (atomicAdd(&cp->done_ctas, 1u) == gridDim.x - 1) {
-      // last CTA out: publish to the host and recycle the record
+    const unsigned long long t1 = dev::globaltimer_ns();
+    if (gridDim.x == 1) {
+      publish_completion(hc, it.req_seq, s_err, t1 - t0);
+    } else {
+      Ctrl *me = reinterpret_cast<Ctrl *>(w.window + static_cast<uint64_t>(w.rank) * w.heap_bytes);
+      Completion *cp = &me->comp[it.req_slot];
+      if (s_err) atomicOr(&cp->retcode, s_err);
+      atomicMin(&cp->t_start, t0);
+      atomicMax(&cp->t_end, t1);
       __threadfence();
-      hc->retcode = cp->retcode;
-      hc->t_start = cp->t_start;
-      hc->t_end = cp->t_end;
-      __threadfence_system();
-      hc->seq = it.req_seq;
-      cp->retcode = 0;
-      cp->done_ctas = 0;
-      cp->t_start = ~0ull;
-      cp->t_end = 0;
+      if (atomicAdd(&cp->done_ctas, 1u) == gridDim.x - 1) {
+        // last CTA out: publish to the host and recycle the record
+        __threadfence();
+        const uint32_t rc = cp->retcode;
+        const unsigned long long dur = cp->t_end - cp->t_start;
+        cp->retcode = 0;
+        cp->done_ctas = 0;
+        cp->t_start = ~0ull;
+        cp->t_end = 0;
+        publish_completion(hc, it.req_seq, rc, dur);
+      }
     }
   }
 }

@@ -771,7 +771,6 @@ ACCLRequest *ACCL::allreduce(BaseBuffer &sendbuf, BaseBuffer &recvbuf, unsigned 
   if (!to_fpga && run_async) warn_async_sync("allreduce");
   auto s = sendbuf.slice(0, count);
   auto r = recvbuf.slice(0, count);
-  if (!from_fpga) s->sync_to_device();
   CCLO::Options o;
   o.scenario = operation::allreduce;
   o.comm = c.index();
@@ -781,6 +780,15 @@ ACCLRequest *ACCL::allreduce(BaseBuffer &sendbuf, BaseBuffer &recvbuf, unsigned 
   o.reduce_function = func;
   o.compress_dtype = compress_dtype;
   o.waitfor = waitfor;
+  if (!from_fpga && !to_fpga && !run_async && config_rdy) {
+    // host-resident operands, blocking call: let the backend overlap H2D / collective / D2H
+    prepare_call(o);
+    if (ACCLRequest *ph = cclo->call_host_pipelined(o)) {
+      check_return_value("allreduce", ph);
+      return ph;
+    }
+  }
+  if (!from_fpga) s->sync_to_device();
   ACCLRequest *h = call_async(o);
   ACCL_FINISH("allreduce", h, run_async, if (!to_fpga) r->sync_from_device());
 }

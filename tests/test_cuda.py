@@ -261,5 +261,18 @@ def test_nvls_paths_when_available(dtype):
         a.reduce_scatter(s, rs, n // w, SUM)
         assert close(rs.host, ref_reduce(w, n, SUM, dtype)[r * (n // w):(r + 1) * (n // w)], tol, tol)
         return a.describe()
-    out = A.run_cuda_ranks(list(range(min(NGPU, 4))), fn, RNDZV, heap_mb=128, max_ctas=8, nvls_min_ranks=2, oneshot_kb=0)
+    out = A.run_cuda_ranks(list(range(min(NGPU, 4))), fn, RNDZV, heap_mb=128, max_ctas=8, nvls_min_ranks=2, oneshot_kb=0, nvls_ops=0xFFFF)
     print(out[0])
+
+
+def test_host_resident_allreduce_is_pipelined_and_correct():
+    n = 12 << 20  # 48 MiB fp32: above the 2 x 16 MiB pipelining threshold, not a multiple of the chunk
+
+    def fn(a, r, w):
+        s, d = a.create_buffer(n + 5), a.create_buffer(n + 5)
+        s.host[:] = float(r + 1)
+        s.host[-1] = 7.0
+        a.allreduce(s, d, n + 5, SUM)   # host-resident operands, blocking: H2D / collective / D2H overlap per chunk
+        assert float(d.host[0]) == sum(range(1, w + 1)) and float(d.host[n]) == sum(range(1, w + 1))
+        assert float(d.host[-1]) == 7.0 * w
+    A.run_cuda_ranks(devices(2), fn, RNDZV, heap_mb=256, max_ctas=8)
