@@ -30,6 +30,8 @@ class module_;
 namespace accl {
 namespace cuda {
 
+constexpr size_t STREAM_FIFO_BYTES = 4u << 20; // device-side stream port capacity per rank (power of two)
+
 struct CudaConfig {
   int device = 0;
   size_t heap_bytes = 1ull << 30;
@@ -124,6 +126,7 @@ private:
   std::mutex m_;
   RequestRegistry requests_;
   std::shared_ptr<BufferStorage> egr_area_;
+  std::shared_ptr<BufferStorage> strm_area_;
   friend struct CudaRequest;
   friend class Engine;
   std::unique_ptr<class Engine> engine_;

@@ -88,8 +88,11 @@ struct Ctrl {
   unsigned long long dev_status[RING_SLOTS]; // slot finished: (ticket + 1) | retcode << 32
   CallDesc dev_ring[RING_SLOTS];
   // ---- device-side stream port (OP0_STREAM / RES_STREAM operands, stream_put)
-  unsigned long long strm_head;   // bytes produced
-  unsigned long long strm_tail;   // bytes consumed
+  unsigned long long strm_head;    // bytes published (readable by the consumer)
+  unsigned long long strm_tail;    // bytes consumed
+  unsigned long long strm_reserve; // bytes reserved by producers (local kernels or peers doing stream_put)
+  uint32_t strm_err;               // sticky error bits raised by stream helper kernels
+  uint32_t strm_pad;
 };
 static_assert(sizeof(Ctrl) <= CTRL_BYTES / 2, "control block too large");
 
@@ -102,6 +105,8 @@ struct DevWorld {
   uint64_t egr_off;    // heap offset of the eager slot area
   uint32_t egr_depth;  // slots per (channel, src)
   uint32_t egr_slot_bytes;
+  uint64_t strm_off;   // heap offset of the device-side stream FIFO (same on every rank)
+  uint64_t strm_cap;   // its capacity in bytes (power of two)
 };
 
 struct WorkItem {
@@ -121,7 +126,11 @@ struct WorkItem {
 };
 constexpr int ISSUE_SLOTS = 4;
 
-enum WorkFlags : uint32_t { WF_USE_MC = 1u << 0, WF_ENGINE = 1u << 1 };
+enum WorkFlags : uint32_t {
+  WF_USE_MC = 1u << 0,
+  WF_ENGINE = 1u << 1,
+  WF_CHAIN = 1u << 2 // not the last kernel of a lowered call: park the error word instead of publishing completion
+};
 
 // eager slot addressing inside a heap
 ACCL_HD uint64_t egr_slot_off(const DevWorld &w, uint32_t ch, uint32_t slot, uint32_t src) {

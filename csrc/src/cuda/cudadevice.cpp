@@ -204,6 +204,10 @@ CudaDevice::CudaDevice(std::shared_ptr<Oob> oob, const CudaConfig &cfg) : oob_(s
   std::memset(hc_host_, 0, sizeof(HostCompletion) * N_REQ_SLOTS);
   ACCL_CUDART(cudaHostGetDevicePointer(reinterpret_cast<void **>(&hc_dev_), hc_host_, 0));
   slot_owner_.assign(N_REQ_SLOTS, nullptr);
+  // device-side stream port: first allocation, so it sits at the same offset in every heap
+  strm_area_ = allocate(STREAM_FIFO_BYTES, bufferKind::p2p);
+  world_.strm_off = strm_area_->device_addr();
+  world_.strm_cap = STREAM_FIFO_BYTES;
   preload_engine_kernels();
   preload_gemm_rs_kernels();
   preload_vadd_kernels();
@@ -219,6 +223,7 @@ CudaDevice::~CudaDevice() {
   engine_.reset();
   cudaStreamSynchronize(stream_);
   egr_area_.reset();
+  strm_area_.reset();
   slot_owner_.clear();
   if (hc_host_) cudaFreeHost(hc_host_);
   heap_.reset();
@@ -406,11 +411,6 @@ ACCLRequest *CudaDevice::start(const Options &options) {
     req->complete(rc, 0);
     return h;
   }
-  if (options.stream_flags != streamFlags::NO_STREAM) {
-    req->immediate = true;
-    req->complete(COLLECTIVE_NOT_IMPLEMENTED, 0);
-    return h;
-  }
   cudaStream_t s = options.stream ? static_cast<cudaStream_t>(options.stream) : op_stream();
   // ---- host-resident operands are staged through heap scratch
   Options o = options;
@@ -432,11 +432,70 @@ ACCLRequest *CudaDevice::start(const Options &options) {
   }
   if (!req->temps.empty()) req->desc = make_call_desc(o);
 
+  // ---- stream operands: lower onto the device-side FIFO (pop before / push after the call)
+  const bool op0_strm = any(options.stream_flags & streamFlags::OP0_STREAM);
+  const bool res_strm = any(options.stream_flags & streamFlags::RES_STREAM);
+  std::unique_ptr<BaseBuffer> strm_bufs[2];
+  uint64_t push_bytes = 0, push_src = 0;
+  uint32_t push_rank = world_.rank;
+  bool put_only = false;
+  if (op0_strm || res_strm) {
+    const operation sop = options.scenario;
+    if (sop != operation::copy && sop != operation::combine && sop != operation::send && sop != operation::recv &&
+        sop != operation::reduce) {
+      req->immediate = true;
+      req->complete(COLLECTIVE_NOT_IMPLEMENTED, 0);
+      return h;
+    }
+    if (op0_strm) {
+      const size_t bytes = static_cast<size_t>(options.count) * dtype_bytes(options.data_type_io_0);
+      auto st = allocate(bytes, bufferKind::p2p);
+      req->temps.push_back(st);
+      strm_bufs[0].reset(new BaseBuffer(st, 0, bytes, options.data_type_io_0));
+      ACCL_CUDART(launch_stream_pop(world_, st->device_addr(), bytes, timeout_us(), s));
+      o.addr_0 = strm_bufs[0].get();
+    }
+    if (res_strm) {
+      const uint32_t ci = o.comm;
+      const uint32_t my_comm_rank = shadow_[exchmem::comm_offset(ci) / 4 + 1];
+      push_bytes = static_cast<uint64_t>(options.count) * dtype_bytes(options.data_type_io_2 != dataType::none ? options.data_type_io_2 : options.data_type_io_0);
+      if (sop == operation::send) {
+        // stream_put: the payload goes straight into the destination rank's FIFO, no matching recv
+        const uint32_t csize = shadow_[exchmem::comm_offset(ci) / 4];
+        if (options.root_src_dst >= csize) {
+          req->immediate = true;
+          req->complete(CONFIG_SWITCH_ERROR, 0);
+          return h;
+        }
+        push_rank = shadow_[exchmem::comm_rank_offset(ci, options.root_src_dst, exchmem::CR_SESSION) / 4];
+        push_src = o.addr_0->address();
+        put_only = true;
+      } else if (sop == operation::reduce && options.root_src_dst != my_comm_rank) {
+        push_bytes = 0; // only the root produces a result
+      } else {
+        auto st = allocate(push_bytes, bufferKind::p2p);
+        req->temps.push_back(st);
+        strm_bufs[1].reset(new BaseBuffer(st, 0, push_bytes, options.data_type_io_2));
+        o.addr_2 = strm_bufs[1].get();
+        push_src = st->device_addr();
+      }
+    }
+    o.stream_flags = streamFlags::NO_STREAM;
+    req->desc = make_call_desc(o);
+  }
+
   WorkItem w;
   uint32_t err = 0;
-  if (!build_work_item(o, req->desc, w, err)) {
+  if (put_only) {
+    CallDesc nd = req->desc;
+    nd.scenario = static_cast<uint32_t>(operation::nop);
+    if (!build_work_item(o, nd, w, err)) err |= CONFIG_SWITCH_ERROR;
+  } else if (!build_work_item(o, req->desc, w, err)) {
+    err |= CONFIG_SWITCH_ERROR;
+  }
+  if (err) {
     req->immediate = true;
-    req->complete(err ? err : static_cast<uint32_t>(CONFIG_SWITCH_ERROR), 0);
+    req->complete(err, 0);
     return h;
   }
   // ---- completion slot
@@ -449,7 +508,23 @@ ACCLRequest *CudaDevice::start(const Options &options) {
   w.req_slot = slot;
   w.req_seq = req->seq;
   req->stream = s;
-  if (engine_) engine_->submit(w, &hc_dev_[slot], s);
+  if (push_bytes) {
+    // lowered call: [op (chained)] -> push -> nop that publishes the completion of the whole chain
+    if (!put_only) {
+      WorkItem first = w;
+      first.flags |= WF_CHAIN;
+      ACCL_CUDART(launch_call(world_, first, &hc_dev_[slot], s));
+    }
+    ACCL_CUDART(launch_stream_push(world_, push_rank, push_src, push_bytes, timeout_us(), s));
+    WorkItem tail;
+    CallDesc nd = req->desc;
+    nd.scenario = static_cast<uint32_t>(operation::nop);
+    uint32_t e2 = 0;
+    build_work_item(o, nd, tail, e2);
+    tail.req_slot = slot;
+    tail.req_seq = req->seq;
+    ACCL_CUDART(launch_call(world_, tail, &hc_dev_[slot], s));
+  } else if (engine_) engine_->submit(w, &hc_dev_[slot], s);
   else ACCL_CUDART(launch_call(world_, w, &hc_dev_[slot], s));
   req->set_status(operationStatus::EXECUTING);
   return h;

@@ -32,8 +32,12 @@ int main(int argc, char **argv) {
           for (unsigned i = 0; i < n; ++i) (*s)[i] = float(i % 13) + r;
           const int nxt = (r + 1) % W, prv = (r + W - 1) % W;
           if (W > 1) {
-            a.free_request(a.send(*s, n, nxt, 5));
+            // async send + blocking recv: legal for eager and for rendezvous (a blocking
+            // rendezvous send before the peer posts its recv would wait forever, as in MPI)
+            ACCLRequest *sreq = a.send(*s, n, nxt, 5, GLOBAL_COMM, false, dataType::none, true);
             a.free_request(a.recv(*d, n, prv, 5));
+            a.wait(sreq);
+            a.free_request(sreq);
             for (unsigned i = 0; i < n; ++i)
               if ((*d)[i] != float(i % 13) + prv) { fails[r]++; break; }
           }

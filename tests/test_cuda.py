@@ -276,3 +276,49 @@ def test_host_resident_allreduce_is_pipelined_and_correct():
         assert float(d.host[0]) == sum(range(1, w + 1)) and float(d.host[n]) == sum(range(1, w + 1))
         assert float(d.host[-1]) == 7.0 * w
     A.run_cuda_ranks(devices(2), fn, RNDZV, heap_mb=256, max_ctas=8)
+
+
+def test_stream_operands_and_stream_put():
+    # the device-side stream port is a FIFO in the heap; results pushed with RES_STREAM are what
+    # OP0_STREAM consumers pop (the reference's emulator runs the same tests with kernel loopback)
+    from accl_b200 import DataType
+    n = 3000
+
+    def fn(a, r, w):
+        s, d = a.create_buffer(n), a.create_buffer(n)
+        s.host[:] = data(n, r)
+        a.copy_to_stream(s, n)
+        a.copy_from_stream(d, n)
+        assert torch.equal(s.host, d.host)
+        a.copy_to_stream(s, n)
+        a.copy_from_to_stream(DataType.float32, n)
+        a.copy_from_stream(d, n)
+        assert torch.equal(s.host, d.host)
+        nxt, prv = (r + 1) % w, (r - 1) % w
+        # memory -> network -> stream -> memory
+        req = a.send(s, n, nxt, tag=9, run_async=True)
+        a.recv_to_stream(DataType.float32, n, prv, tag=9)
+        req.wait()
+        a.copy_from_stream(d, n)
+        assert torch.equal(d.host, data(n, prv))
+        # memory -> stream -> network -> memory
+        a.copy_to_stream(s, n)
+        req = a.send_from_stream(DataType.float32, n, nxt, tag=11, run_async=True)
+        a.recv(d, n, prv, tag=11)
+        req.wait()
+        assert torch.equal(d.host, data(n, prv))
+        # one-sided put into the peer's stream, no matching recv
+        a.barrier()
+        a.stream_put(s, n, nxt, 9)
+        a.copy_from_stream(d, n)
+        assert torch.equal(d.host, data(n, prv))
+        # reduce: stream -> memory and memory -> stream
+        a.copy_to_stream(s, n)
+        a.reduce_stream2mem(DataType.float32, d, n, 0, SUM)
+        if r == 0:
+            assert close(d.host, ref_reduce(w, n, SUM), 1e-5, 1e-5)
+        a.reduce_mem2stream(s, DataType.float32, n, 0, SUM)
+        if r == 0:
+            a.copy_from_stream(d, n)
+            assert close(d.host, ref_reduce(w, n, SUM), 1e-5, 1e-5)
+    run(2, fn, EAGER)

@@ -77,3 +77,37 @@ def test_vadd_plugin_issues_allreduce_from_the_device():
         assert torch.equal(out.dev.cpu(), ref)
 
     A.run_cuda_ranks(devices(2), fn, CFG, heap_mb=64, max_ctas=4, engine=True)
+
+
+def test_tensor_group_and_row_parallel_linear():
+    from accl_b200.parallel import TensorGroup, RowParallelLinear, ring_exchange
+    M, K, N = 512, 128, 256
+
+    def fn(a, r, w):
+        g = TensorGroup(a)
+        dev = torch.device("cuda", a.cuda_device)
+        t = torch.full((1000,), float(r + 1), device=dev)          # ordinary torch tensor: staged through the heap
+        g.all_reduce(t)
+        assert torch.all(t == sum(range(1, w + 1)))
+        h = g.empty(64, dtype=torch.float32)                        # heap tensor: zero-copy
+        h.fill_(float(r))
+        g.all_reduce(h)
+        assert torch.all(h == sum(range(w)))
+        out = torch.empty(64 * w, device=dev)
+        g.all_gather_into_tensor(out, torch.full((64,), float(r), device=dev))
+        assert torch.equal(out.view(w, 64)[:, 0].cpu(), torch.arange(w, dtype=torch.float32))
+        a_blk, b_blk = torch.full((32,), float(r), device=dev), torch.empty(32, device=dev)
+        ring_exchange(g, a_blk, b_blk, tag=4)
+        assert torch.all(b_blk == float((r - 1) % w))
+        lin = RowParallelLinear(g, K, N)
+        gen = torch.Generator().manual_seed(5 + r)
+        x = (torch.randn(M * w, K, generator=gen) * 0.5).bfloat16().to(dev)
+        y = lin(x)
+        torch.cuda.current_stream().synchronize()
+        return y.float().cpu(), x.float().cpu(), lin.weight.data.float().cpu()
+
+    res = A.run_cuda_ranks(devices(2), fn, CFG, heap_mb=64, max_ctas=4)
+    full = sum(x @ wt.t() for _, x, wt in res)
+    rows = full.shape[0] // 2
+    for r, (y, _, _) in enumerate(res):
+        assert close(y, full[r * rows:(r + 1) * rows], 2e-2, 3e-1)
