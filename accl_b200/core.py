@@ -381,7 +381,7 @@ def _prepare_cuda_env():
     # engine pinned while launching brand-new kernels, export CUDA_MODULE_LOADING=EAGER.
 
 
-def cuda_world(devices, heap_mb=256, multicast=True, max_ctas=8, engine=False, nvls_min_ranks=3, oneshot_kb=512,
+def cuda_world(devices, heap_mb=256, multicast=True, max_ctas=8, engine=False, nvls_min_ranks=3, oneshot_kb=2048,
                nvls_ops=-1):
     """In-process world on real GPUs: rank i drives devices[i] (a device may
     appear several times: ranks then share that GPU, without NVLS)."""
@@ -391,7 +391,7 @@ def cuda_world(devices, heap_mb=256, multicast=True, max_ctas=8, engine=False, n
 
 
 def cuda_rank(rank=None, world_size=None, device=None, addr=None, port=None, heap_mb=1024, multicast=True,
-              max_ctas=32, engine=False, nvls_min_ranks=3, oneshot_kb=512, nvls_ops=-1):
+              max_ctas=32, engine=False, nvls_min_ranks=3, oneshot_kb=2048, nvls_ops=-1):
     """One rank per process (torchrun): RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT."""
     _prepare_cuda_env()
     rank = int(os.environ.get("RANK", 0)) if rank is None else rank

@@ -39,7 +39,7 @@ struct CudaConfig {
   int max_ctas = 32;           // CTAs a single call may use (== sync channels used)
   int nvls_min_ranks = 3;      // below this, peer loads/stores beat the switch round trip
   size_t host_pipeline_chunk = 16u << 20; // chunk size of the pipelined host-operand path (0 = off)
-  size_t oneshot_max_bytes = 512 << 10; // allreduce: pull-everything one-shot up to this size
+  size_t oneshot_max_bytes = 2048 << 10; // allreduce: pull-everything one-shot while bytes x ranks <= this
   uint32_t nvls_ops = NVLS_OPS_DEFAULT;  // which operations may use multimem (bit = operation code)
   bool engine = false;         // route calls through the persistent engine kernel
   int engine_idle_us = 200;    // engine kernel parks itself after this idle time (0 = never)

@@ -75,7 +75,8 @@ ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
   const bool nvls = cfg.has_mc && P >= cfg.nvls_min_ranks && P == cfg.heap_world &&
                     ((cfg.nvls_ops >> static_cast<uint32_t>(op)) & 1u);
   w.algo = nvls ? ALGO_NVLS : ALGO_P2P;
-  if (op == operation::allreduce && ubytes <= cfg.oneshot_max_bytes) w.algo = ALGO_P2P_ONESHOT;
+  // one-shot (everybody pulls everything) moves P x the bytes of two-shot: only while latency dominates
+  if (op == operation::allreduce && ubytes * P <= cfg.oneshot_max_bytes) w.algo = ALGO_P2P_ONESHOT;
   if (op == operation::send || op == operation::recv) w.algo = ALGO_P2P;
   w.n_ctas = plan_ctas(moved, 128u << 10, cap);
 }

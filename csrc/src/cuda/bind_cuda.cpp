@@ -63,7 +63,7 @@ void bind_cuda(py::module_ &m) {
     for (auto &d : devs) out.emplace_back(new ACCL(std::move(d)));
     return out;
   }, py::arg("devices"), py::arg("heap_mb") = 256, py::arg("multicast") = true, py::arg("max_ctas") = 32,
-        py::arg("engine") = false, py::arg("nvls_min_ranks") = 3, py::arg("oneshot_kb") = 512, py::arg("nvls_ops") = -1,
+        py::arg("engine") = false, py::arg("nvls_min_ranks") = 3, py::arg("oneshot_kb") = 2048, py::arg("nvls_ops") = -1,
         py::call_guard<py::gil_scoped_release>());
   // one rank per process; bootstrap over a private TCP rendezvous on addr:port
   m.def("make_cuda_rank", [](int rank, int world, int device, const std::string &addr, int port, size_t heap_mb,
@@ -74,7 +74,7 @@ void bind_cuda(py::module_ &m) {
     return std::unique_ptr<ACCL>(new ACCL(std::move(dev)));
   }, py::arg("rank"), py::arg("world_size"), py::arg("device"), py::arg("addr") = "127.0.0.1", py::arg("port") = 29637,
         py::arg("heap_mb") = 1024, py::arg("multicast") = true, py::arg("max_ctas") = 32, py::arg("engine") = false,
-        py::arg("nvls_min_ranks") = 3, py::arg("oneshot_kb") = 512, py::arg("nvls_ops") = -1,
+        py::arg("nvls_min_ranks") = 3, py::arg("oneshot_kb") = 2048, py::arg("nvls_ops") = -1,
         py::call_guard<py::gil_scoped_release>());
 }
 

@@ -400,12 +400,13 @@ template <NvOp OP, bool MC_OUT>
 __device__ __forceinline__ void nvls_reduce_range(const char *mc_in, char *out, size_t v0, size_t v1, int cta, int nctas) {
   const size_t stride = static_cast<size_t>(nctas) * blockDim.x;
   size_t i = v0 + static_cast<size_t>(cta) * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < v1; i += 4 * stride) {
-    Vec16 v[4];
+  constexpr int U = 8; // in-switch reductions have a long round trip: keep 8 x 16 B per thread in flight
+  for (; i + (U - 1) * stride < v1; i += U * stride) {
+    Vec16 v[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = nv_ld<OP>(mc_in + (i + u * stride) * 16);
+    for (int u = 0; u < U; ++u) v[u] = nv_ld<OP>(mc_in + (i + u * stride) * 16);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       if (MC_OUT) multimem_st16(out + (i + u * stride) * 16, v[u]);
       else st_stream(out + (i + u * stride) * 16, v[u]);
     }
@@ -434,12 +435,12 @@ __device__ __forceinline__ void nvls_reduce_dispatch(NvOp op, const char *mc_in,
 __device__ __forceinline__ void nvls_bcast_range(const char *src, char *mc_out, size_t nvec, int cta, int nctas) {
   const size_t stride = static_cast<size_t>(nctas) * blockDim.x;
   size_t i = static_cast<size_t>(cta) * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < nvec; i += 4 * stride) {
-    Vec16 v[4];
+  for (; i + 7 * stride < nvec; i += 8 * stride) {
+    Vec16 v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld_stream(src + (i + u * stride) * 16);
+    for (int u = 0; u < 8; ++u) v[u] = ld_stream(src + (i + u * stride) * 16);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) multimem_st16(mc_out + (i + u * stride) * 16, v[u]);
+    for (int u = 0; u < 8; ++u) multimem_st16(mc_out + (i + u * stride) * 16, v[u]);
   }
   for (; i < nvec; i += stride) multimem_st16(mc_out + i * 16, ld_stream(src + i * 16));
 }
