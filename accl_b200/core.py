@@ -390,6 +390,24 @@ def cuda_world(devices, heap_mb=256, multicast=True, max_ctas=8, engine=False, n
     return [Accl(a, r, len(devices), cuda_device=devices[r]) for r, a in enumerate(impls)]
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this process to the CPUs nearest to `device` (NVML affinity) so that pinned staging
+    buffers and the launch path stay on the GPU's NUMA node.  Best effort; returns the CPU set."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {i * 64 + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # noqa: BLE001
+        return set()
+
+
 def cuda_rank(rank=None, world_size=None, device=None, addr=None, port=None, heap_mb=1024, multicast=True,
               max_ctas=32, engine=False, nvls_min_ranks=3, oneshot_kb=2048, nvls_ops=-1):
     """One rank per process (torchrun): RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT."""
@@ -402,6 +420,8 @@ def cuda_rank(rank=None, world_size=None, device=None, addr=None, port=None, hea
         addr = "127.0.0.1"
     if port is None:
         port = int(os.environ.get("ACCL_PORT", int(os.environ.get("MASTER_PORT", 29500)) + 137))
+    if os.environ.get("ACCL_BIND_NUMA", "1") != "0":
+        bind_to_gpu_numa_node(device)
     impl = _C.make_cuda_rank(rank, world_size, device, addr, port, heap_mb, multicast, max_ctas, engine,
                              nvls_min_ranks, oneshot_kb, nvls_ops)
     return Accl(impl, rank, world_size, cuda_device=device)

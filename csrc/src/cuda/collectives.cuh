@@ -533,6 +533,8 @@ __device__ __noinline__ void rv_reduce_scatter(const Ctx &c, uint64_t *s_off0, u
   chan_sync(c, false, 0, 0, nullptr, nullptr);
 }
 
+__device__ __noinline__ void rv_bcast_pipelined(const Ctx &c, const uint64_t *s_off);
+
 // push-style data movement shared by allgather / bcast / scatter / gather / alltoall
 __device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_off0, uint64_t *s_off2) {
   const WorkItem &it = c.it;
@@ -557,7 +559,9 @@ __device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_o
       }
       break;
     case EP_BCAST:
-      if (me == root) {
+      if (mc_ok && P >= 3 && blk >= (4u << 20) && all_equal(s_off0, P)) {
+        rv_bcast_pipelined(c, s_off2);
+      } else if (me == root) {
         if (mc_ok) {
           // the multicast store also rewrites the root's own copy with identical bytes
           nvls_bcast_range(src, c.w.mc + s_off2[0], blk / 16, c.cta, c.nctas);
@@ -594,30 +598,94 @@ __device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_o
   chan_sync(c, false, 0, 0, nullptr, nullptr);
 }
 
-// reduce to root: the root pulls (or lets the switch reduce) everything
+// reduce to root.  Small: the root pulls (or lets the switch reduce) everything.  Large
+// (P >= 3): the P-1 other ranks each reduce one slice and store it into the root's buffer,
+// so the root's inbound link carries N bytes instead of (P-1) N.
 __device__ __noinline__ void rv_reduce(const Ctx &c, uint64_t *s_off0, uint64_t *s_off2) {
   const WorkItem &it = c.it;
   const uint32_t P = c.P(), me = c.r(), root = it.desc.root_src_dst;
   chan_sync(c, true, it.desc.addr0(), it.desc.addr2(), s_off0, s_off2);
-  if (*c.err == 0 && me == root) {
+  if (*c.err == 0) {
     const size_t es = esize(it.udtype), count = it.desc.count;
     const NvOp nop = nvls_op(it.udtype, it.desc.function);
-    char *dst = c.heap(c.w.rank) + it.desc.addr2();
-    const bool sym = all_equal(s_off0, P) && (s_off0[0] & 15) == 0 && (it.desc.addr2() & 15) == 0;
+    const bool sym = all_equal(s_off0, P) && (s_off0[0] & 15) == 0 && (s_off2[root] & 15) == 0;
+    const bool use_mc = (it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && nop != NvOp::none && sym;
+    char *root_dst = c.heap(c.g(root)) + s_off2[root];
+    const size_t nvec = count * es / 16;
+    const bool distributed = P >= 3 && count * es >= (1u << 20) && (s_off2[root] & 15) == 0;
     size_t done = 0;
-    if ((it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && nop != NvOp::none && sym) {
-      const size_t nvec = count * es / 16;
-      nvls_reduce_dispatch<false>(nop, c.w.mc + s_off0[0], dst, 0, nvec, c.cta, c.nctas);
+    if (distributed) {
+      if (me != root) {
+        const uint32_t j = (me + P - root - 1) % P; // my index among the P-1 workers
+        const size_t per = (nvec + (P - 1) - 1) / (P - 1);
+        const size_t v0 = j * per < nvec ? j * per : nvec, v1 = v0 + per < nvec ? v0 + per : nvec;
+        if (use_mc) {
+          nvls_reduce_dispatch<false>(nop, c.w.mc + s_off0[0], root_dst, v0, v1, c.cta, c.nctas);
+        } else if ((s_off0[0] & 15) == 0 || true) {
+          fill_table(c, s_off0, nullptr, v0 * 16, 0, true);
+          if (threadIdx.x == 0) c.tab->dst[0] = root_dst + v0 * 16;
+          __syncthreads();
+          reduce_dispatch(c.tab, static_cast<int>(P), 1, (v1 - v0) * (16 / es), it.udtype, it.desc.function, c.cta, c.nctas, c.err);
+        }
+      }
+      done = nvec * 16 / es; // the sub-vector tail (if any) is reduced by the root below
+    } else if (me == root && use_mc) {
+      nvls_reduce_dispatch<false>(nop, c.w.mc + s_off0[0], root_dst, 0, nvec, c.cta, c.nctas);
       done = nvec * 16 / es;
     }
-    if (done < count) {
+    if (me == root && done < count) {
       fill_table(c, s_off0, nullptr, done * es, 0, false);
-      if (threadIdx.x == 0) c.tab->dst[0] = dst + done * es;
+      if (threadIdx.x == 0) c.tab->dst[0] = root_dst + done * es;
       __syncthreads();
       reduce_dispatch(c.tab, static_cast<int>(P), 1, count - done, it.udtype, it.desc.function, c.cta, c.nctas, c.err);
     }
   }
   chan_sync(c, false, 0, 0, nullptr, nullptr);
+}
+
+// Large broadcast through the switch, software-pipelined: the root deals slice j of its buffer to
+// worker j with peer stores (root outbound = N in total), worker j re-broadcasts what it received
+// with multimem.st (every rank's inbound = N).  Chunk c is multicast while chunk c+1 is dealt.
+__device__ __noinline__ void rv_bcast_pipelined(const Ctx &c, const uint64_t *s_off) {
+  const WorkItem &it = c.it;
+  const uint32_t P = c.P(), me = c.r(), root = it.desc.root_src_dst;
+  const size_t nvec = static_cast<size_t>(it.desc.count) * esize(it.udtype) / 16;
+  const uint32_t W = P - 1;                       // workers
+  const size_t per_slice = (nvec + W - 1) / W;    // vectors per worker slice
+  const size_t per_cta = (per_slice + c.nctas - 1) / c.nctas;
+  const size_t CH = 4096;                         // 64 KiB per (slice, CTA) per step
+  const size_t steps = (per_cta + CH - 1) / CH;
+  const uint32_t j_me = (me + P - root - 1) % P;  // my worker index (unused on the root)
+  const char *src = c.heap(c.w.rank) + s_off[me];
+  for (size_t st = 0; st <= steps; ++st) {
+    if (me == root && st < steps) {
+      for (uint32_t k = 0; k < W; ++k) {
+        const uint32_t j = (k + static_cast<uint32_t>(c.cta)) % W; // CTAs start on different workers
+        const uint32_t q = (root + 1 + j) % P;
+        const size_t a = j * per_slice + static_cast<size_t>(c.cta) * per_cta + st * CH;
+        size_t b = a + CH;
+        const size_t lim_cta = j * per_slice + (static_cast<size_t>(c.cta) + 1) * per_cta;
+        const size_t lim_slice = (j + 1) * per_slice < nvec ? (j + 1) * per_slice : nvec;
+        if (b > lim_cta) b = lim_cta;
+        if (b > lim_slice) b = lim_slice;
+        if (a < b) copy_simple(c.heap(c.g(q)) + s_off[q] + a * 16, src + a * 16, (b - a) * 16, 0, 1);
+      }
+    } else if (me != root && st >= 1) {
+      const size_t a = j_me * per_slice + static_cast<size_t>(c.cta) * per_cta + (st - 1) * CH;
+      size_t b = a + CH;
+      const size_t lim_cta = j_me * per_slice + (static_cast<size_t>(c.cta) + 1) * per_cta;
+      const size_t lim_slice = (j_me + 1) * per_slice < nvec ? (j_me + 1) * per_slice : nvec;
+      if (b > lim_cta) b = lim_cta;
+      if (b > lim_slice) b = lim_slice;
+      // coherent read of what the root stored a step ago, then fan out through the switch
+      if (a < b) {
+        const char *in = src + a * 16;
+        char *out = c.w.mc + s_off[0] + a * 16;
+        for (size_t i = threadIdx.x; i < b - a; i += blockDim.x) multimem_st16(out + i * 16, ld_relaxed_sys16(in + i * 16));
+      }
+    }
+    chan_sync(c, false, 0, 0, nullptr, nullptr);
+  }
 }
 
 // rendezvous send / recv: a pair of ranks meets on the pads, the receiver

@@ -322,3 +322,39 @@ def test_stream_operands_and_stream_put():
             a.copy_from_stream(d, n)
             assert close(d.host, ref_reduce(w, n, SUM), 1e-5, 1e-5)
     run(2, fn, EAGER)
+
+
+def test_large_reduce_is_distributed_over_workers():
+    n = (1 << 19) + 3   # > 1 MiB: the non-root ranks each reduce a slice and store it into the root
+
+    def fn(a, r, w):
+        for root in (0, w - 1):
+            s, d = a.create_buffer(n), a.create_buffer(n)
+            s.host[:] = data(n, r, salt=root)
+            a.reduce(s, d, n, root, SUM)
+            if r == root:
+                assert close(d.host, ref_reduce(w, n, SUM, salt=root), 1e-5, 1e-4)
+    run(3, fn, RNDZV)
+
+
+@pytest.mark.multigpu
+@pytest.mark.skipif(NGPU < 3, reason="pipelined NVLS broadcast needs >= 3 GPUs")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_large_bcast_and_reduce_through_the_switch(dtype):
+    n = (6 << 20) + 8   # 24 MiB fp32: pipelined scatter + multimem.st broadcast; distributed NVLS reduce
+    w_ = min(NGPU, 8)
+
+    def fn(a, r, w):
+        for root in (0, w - 1):
+            b = a.create_buffer(n, dtype)
+            if r == root:
+                b.host[:] = data(n, root, dtype, salt=root)
+            a.bcast(b, n, root)
+            assert torch.equal(b.host, data(n, root, dtype, salt=root))
+            s, d = a.create_buffer(n, dtype), a.create_buffer(n, dtype)
+            s.host[:] = data(n, r, dtype, salt=root)
+            a.reduce(s, d, n, root, SUM)
+            if r == root:
+                tol = 1e-4 if dtype == torch.float32 else 2e-1
+                assert close(d.host, ref_reduce(w, n, SUM, dtype, salt=root), tol, tol)
+    A.run_cuda_ranks(list(range(w_)), fn, RNDZV, heap_mb=512, max_ctas=16)
