@@ -547,6 +547,8 @@ __device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_o
     const char *src = c.heap(c.w.rank) + it.desc.addr0();
     const bool mc_ok = (it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && all_equal(s_off2, P) && (blk & 15) == 0 &&
                        (s_off2[0] & 15) == 0 && (it.desc.addr0() & 15) == 0;
+    bool bcast_pipelined = pat == EP_BCAST && P >= 3 && blk >= (32u << 20) && (blk & 15) == 0;
+    for (uint32_t q = 0; q < P; ++q) bcast_pipelined = bcast_pipelined && (s_off2[q] & 15) == 0;
     switch (pat) {
     case EP_ALLGATHER:
       if (mc_ok) {
@@ -559,7 +561,7 @@ __device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_o
       }
       break;
     case EP_BCAST:
-      if (mc_ok && P >= 3 && blk >= (4u << 20) && all_equal(s_off0, P)) {
+      if (bcast_pipelined) {
         rv_bcast_pipelined(c, s_off2);
       } else if (me == root) {
         if (mc_ok) {
@@ -619,9 +621,9 @@ __device__ __noinline__ void rv_reduce(const Ctx &c, uint64_t *s_off0, uint64_t 
         const uint32_t j = (me + P - root - 1) % P; // my index among the P-1 workers
         const size_t per = (nvec + (P - 1) - 1) / (P - 1);
         const size_t v0 = j * per < nvec ? j * per : nvec, v1 = v0 + per < nvec ? v0 + per : nvec;
-        if (use_mc) {
-          nvls_reduce_dispatch<false>(nop, c.w.mc + s_off0[0], root_dst, v0, v1, c.cta, c.nctas);
-        } else if ((s_off0[0] & 15) == 0 || true) {
+        {
+          // peer pulls: every worker's inbound link carries ~N, like the root's; measured faster than
+          // letting the switch reduce (profiles/SWEEPS.md: multimem.ld_reduce tops out near 470 GB/s here)
           fill_table(c, s_off0, nullptr, v0 * 16, 0, true);
           if (threadIdx.x == 0) c.tab->dst[0] = root_dst + v0 * 16;
           __syncthreads();
@@ -643,9 +645,10 @@ __device__ __noinline__ void rv_reduce(const Ctx &c, uint64_t *s_off0, uint64_t 
   chan_sync(c, false, 0, 0, nullptr, nullptr);
 }
 
-// Large broadcast through the switch, software-pipelined: the root deals slice j of its buffer to
-// worker j with peer stores (root outbound = N in total), worker j re-broadcasts what it received
-// with multimem.st (every rank's inbound = N).  Chunk c is multicast while chunk c+1 is dealt.
+// Large broadcast, software-pipelined in two overlapping stages: the root deals slice j of its
+// buffer to worker j (root outbound = N in total); worker j forwards what it received to the other
+// workers (worker inbound = N, outbound = N (P-2)/(P-1)).  Chunk c is forwarded while chunk c+1 is
+// dealt, each CTA running its own stripe of every slice with its own flags.
 __device__ __noinline__ void rv_bcast_pipelined(const Ctx &c, const uint64_t *s_off) {
   const WorkItem &it = c.it;
   const uint32_t P = c.P(), me = c.r(), root = it.desc.root_src_dst;
@@ -653,35 +656,42 @@ __device__ __noinline__ void rv_bcast_pipelined(const Ctx &c, const uint64_t *s_
   const uint32_t W = P - 1;                       // workers
   const size_t per_slice = (nvec + W - 1) / W;    // vectors per worker slice
   const size_t per_cta = (per_slice + c.nctas - 1) / c.nctas;
-  const size_t CH = 4096;                         // 64 KiB per (slice, CTA) per step
+  const size_t CH = 16384;                        // 256 KiB per (slice, CTA) per step
   const size_t steps = (per_cta + CH - 1) / CH;
   const uint32_t j_me = (me + P - root - 1) % P;  // my worker index (unused on the root)
   const char *src = c.heap(c.w.rank) + s_off[me];
+  auto range = [&](uint32_t j, size_t step, size_t &a, size_t &b) {
+    a = j * per_slice + static_cast<size_t>(c.cta) * per_cta + step * CH;
+    b = a + CH;
+    const size_t lim_cta = j * per_slice + (static_cast<size_t>(c.cta) + 1) * per_cta;
+    const size_t lim_slice = (j + 1) * per_slice < nvec ? (j + 1) * per_slice : nvec;
+    if (b > lim_cta) b = lim_cta;
+    if (b > lim_slice) b = lim_slice;
+  };
   for (size_t st = 0; st <= steps; ++st) {
     if (me == root && st < steps) {
       for (uint32_t k = 0; k < W; ++k) {
         const uint32_t j = (k + static_cast<uint32_t>(c.cta)) % W; // CTAs start on different workers
         const uint32_t q = (root + 1 + j) % P;
-        const size_t a = j * per_slice + static_cast<size_t>(c.cta) * per_cta + st * CH;
-        size_t b = a + CH;
-        const size_t lim_cta = j * per_slice + (static_cast<size_t>(c.cta) + 1) * per_cta;
-        const size_t lim_slice = (j + 1) * per_slice < nvec ? (j + 1) * per_slice : nvec;
-        if (b > lim_cta) b = lim_cta;
-        if (b > lim_slice) b = lim_slice;
+        size_t a, b;
+        range(j, st, a, b);
         if (a < b) copy_simple(c.heap(c.g(q)) + s_off[q] + a * 16, src + a * 16, (b - a) * 16, 0, 1);
       }
-    } else if (me != root && st >= 1) {
-      const size_t a = j_me * per_slice + static_cast<size_t>(c.cta) * per_cta + (st - 1) * CH;
-      size_t b = a + CH;
-      const size_t lim_cta = j_me * per_slice + (static_cast<size_t>(c.cta) + 1) * per_cta;
-      const size_t lim_slice = (j_me + 1) * per_slice < nvec ? (j_me + 1) * per_slice : nvec;
-      if (b > lim_cta) b = lim_cta;
-      if (b > lim_slice) b = lim_slice;
-      // coherent read of what the root stored a step ago, then fan out through the switch
+    } else if (me != root && st >= 1 && W >= 2) {
+      size_t a, b;
+      range(j_me, st - 1, a, b);
       if (a < b) {
-        const char *in = src + a * 16;
-        char *out = c.w.mc + s_off[0] + a * 16;
-        for (size_t i = threadIdx.x; i < b - a; i += blockDim.x) multimem_st16(out + i * 16, ld_relaxed_sys16(in + i * 16));
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int nd = 0;
+          for (uint32_t k = 1; k < W; ++k) { // the other workers, starting after me
+            const uint32_t q = (root + 1 + (j_me + k) % W) % P;
+            c.tab->dst[nd++] = c.heap(c.g(q)) + s_off[q] + a * 16;
+          }
+          c.tab->src[0] = src + a * 16; // what the root stored here one step ago
+        }
+        __syncthreads();
+        copy_dispatch(c.tab, static_cast<int>(W) - 1, (b - a) * 16, 0, 1);
       }
     }
     chan_sync(c, false, 0, 0, nullptr, nullptr);

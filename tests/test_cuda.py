@@ -358,3 +358,16 @@ def test_large_bcast_and_reduce_through_the_switch(dtype):
                 tol = 1e-4 if dtype == torch.float32 else 2e-1
                 assert close(d.host, ref_reduce(w, n, SUM, dtype, salt=root), tol, tol)
     A.run_cuda_ranks(list(range(w_)), fn, RNDZV, heap_mb=512, max_ctas=16)
+
+
+def test_large_bcast_is_pipelined_over_workers():
+    n = (9 << 20) + 4   # 36 MiB fp32 (>= 32 MiB): the root deals slices, the workers forward them
+
+    def fn(a, r, w):
+        for root in (0, 1):
+            b = a.create_buffer(n)
+            if r == root:
+                b.host[:] = data(n, root, salt=root)
+            a.bcast(b, n, root)
+            assert torch.equal(b.host, data(n, root, salt=root))
+    A.run_cuda_ranks(devices(3), fn, RNDZV, heap_mb=256, max_ctas=8)
