@@ -84,7 +84,7 @@ def main():
     ap.add_argument("--impl", default="accl", choices=["accl", "reference", "nccl"])
     ap.add_argument("--bytes", type=int, default=256 << 20)
     ap.add_argument("--dtype", default="float32")
-    ap.add_argument("--max-ctas", type=int, default=int(os.environ.get("ACCL_MAX_CTAS", 64)))
+    ap.add_argument("--max-ctas", type=int, default=int(os.environ.get("ACCL_MAX_CTAS", 128)))
     ap.add_argument("--engine", action="store_true", help="route calls through the persistent engine kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-nccl", action="store_true")

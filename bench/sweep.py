@@ -36,7 +36,7 @@ def main():
     ap.add_argument("--max-log2", type=int, default=30)
     ap.add_argument("--step", type=int, default=2)
     ap.add_argument("--dtype", default="float32")
-    ap.add_argument("--max-ctas", type=int, default=64)
+    ap.add_argument("--max-ctas", type=int, default=128)
     ap.add_argument("--egr-kb", type=int, default=64, help="eager threshold / slot size in KiB")
     ap.add_argument("--oneshot-kb", type=int, default=2048)
     ap.add_argument("--nvls-min-ranks", type=int, default=3)

@@ -17,7 +17,7 @@
 namespace accl {
 namespace cuda {
 
-constexpr int MAX_CH = 64;        // sync channels == max CTAs cooperating on one call
+constexpr int MAX_CH = 160;       // sync channels == max CTAs cooperating on one call (one per SM and a few spare)
 constexpr int EGR_CH = 16;        // channels usable by eager (slot-based) transfers
 constexpr int EGR_DEPTH_MAX = 16; // slots per (channel, src): the eager RX buffers
 constexpr int N_REQ_SLOTS = 256;  // completion records

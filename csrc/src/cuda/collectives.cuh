@@ -547,7 +547,7 @@ __device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_o
     const char *src = c.heap(c.w.rank) + it.desc.addr0();
     const bool mc_ok = (it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && all_equal(s_off2, P) && (blk & 15) == 0 &&
                        (s_off2[0] & 15) == 0 && (it.desc.addr0() & 15) == 0;
-    bool bcast_pipelined = pat == EP_BCAST && P >= 3 && blk >= (32u << 20) && (blk & 15) == 0;
+    bool bcast_pipelined = pat == EP_BCAST && P >= 3 && blk >= (16u << 20) && (blk & 15) == 0;
     for (uint32_t q = 0; q < P; ++q) bcast_pipelined = bcast_pipelined && (s_off2[q] & 15) == 0;
     switch (pat) {
     case EP_ALLGATHER:
@@ -656,7 +656,9 @@ __device__ __noinline__ void rv_bcast_pipelined(const Ctx &c, const uint64_t *s_
   const uint32_t W = P - 1;                       // workers
   const size_t per_slice = (nvec + W - 1) / W;    // vectors per worker slice
   const size_t per_cta = (per_slice + c.nctas - 1) / c.nctas;
-  const size_t CH = 16384;                        // 256 KiB per (slice, CTA) per step
+  // per (slice, CTA) step: about 1/8 of the stripe, between 32 KiB and 256 KiB (pipeline depth vs sync cost)
+  size_t CH = per_cta / 8;
+  CH = CH < 2048 ? 2048 : (CH > 16384 ? 16384 : CH);
   const size_t steps = (per_cta + CH - 1) / CH;
   const uint32_t j_me = (me + P - root - 1) % P;  // my worker index (unused on the root)
   const char *src = c.heap(c.w.rank) + s_off[me];

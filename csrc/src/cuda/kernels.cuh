@@ -197,6 +197,53 @@ template <typename T> struct VecOf {
   }
 };
 
+// 16-bit floats: widen / narrow two lanes per 32-bit word (bf16 -> f32 is a shift, the narrowing
+// is one cvt.rn.*x2 per pair) instead of eight scalar conversions per 16 bytes.  The SM reduce
+// paths are ALU-limited for 16-bit types otherwise.
+template <> struct VecOf<__nv_bfloat16> {
+  static constexpr int N = 8;
+  using A = float;
+  static __device__ __forceinline__ void unpack(const Vec16 &v, A (&a)[N]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[2 * i] = __uint_as_float(w[i] << 16);
+      a[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  static __device__ __forceinline__ Vec16 pack(const A (&a)[N]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 p = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t *>(&p);
+    }
+    return Vec16{w[0], w[1], w[2], w[3]};
+  }
+};
+template <> struct VecOf<__half> {
+  static constexpr int N = 8;
+  using A = float;
+  static __device__ __forceinline__ void unpack(const Vec16 &v, A (&a)[N]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
+      a[2 * i] = f.x;
+      a[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ Vec16 pack(const A (&a)[N]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 p = __floats2half2_rn(a[2 * i], a[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t *>(&p);
+    }
+    return Vec16{w[0], w[1], w[2], w[3]};
+  }
+};
+
 // Pointer table of one data-movement step.  Lives in shared memory so that
 // rank-indexed accesses never turn into local-memory arrays.
 struct PtrTable {
