@@ -547,7 +547,7 @@ __device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_o
     const char *src = c.heap(c.w.rank) + it.desc.addr0();
     const bool mc_ok = (it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && all_equal(s_off2, P) && (blk & 15) == 0 &&
                        (s_off2[0] & 15) == 0 && (it.desc.addr0() & 15) == 0;
-    bool bcast_pipelined = pat == EP_BCAST && P >= 3 && blk >= (16u << 20) && (blk & 15) == 0;
+    bool bcast_pipelined = pat == EP_BCAST && P >= 3 && blk >= (128u << 20) && (blk & 15) == 0;
     for (uint32_t q = 0; q < P; ++q) bcast_pipelined = bcast_pipelined && (s_off2[q] & 15) == 0;
     switch (pat) {
     case EP_ALLGATHER:

@@ -361,7 +361,7 @@ def test_large_bcast_and_reduce_through_the_switch(dtype):
 
 
 def test_large_bcast_is_pipelined_over_workers():
-    n = (9 << 20) + 4   # 36 MiB fp32 (>= 32 MiB): the root deals slices, the workers forward them
+    n = (33 << 20) + 4   # 132 MiB fp32 (>= 128 MiB): the root deals slices, the workers forward them
 
     def fn(a, r, w):
         for root in (0, 1):
@@ -370,4 +370,4 @@ def test_large_bcast_is_pipelined_over_workers():
                 b.host[:] = data(n, root, salt=root)
             a.bcast(b, n, root)
             assert torch.equal(b.host, data(n, root, salt=root))
-    A.run_cuda_ranks(devices(3), fn, RNDZV, heap_mb=256, max_ctas=8)
+    A.run_cuda_ranks(devices(3), fn, RNDZV, heap_mb=512, max_ctas=8)
