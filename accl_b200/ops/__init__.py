@@ -1,1 +1,1 @@
-from .plugins import gemm_reduce_scatter, vadd_allreduce  # noqa: F401
+from .plugins import gemm_reduce_scatter, stream_loopback, vadd_allreduce  # noqa: F401

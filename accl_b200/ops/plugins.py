@@ -46,3 +46,16 @@ def vadd_allreduce(accl: Accl, x: Buffer, y: Buffer, out: Buffer, tmp: Buffer = 
     _C.vadd_allreduce(accl.impl, x.impl, y.impl, tmp.impl, out.impl, count, status.data_ptr(), _stream_handle(accl))
     status._keep = tmp
     return status
+
+
+def stream_loopback(accl: Accl, count: int, add_one: bool = False, scratch: Buffer = None):
+    """Run the loopback user kernel on this rank's stream port: pull `count` fp32 words that a previous
+    `copy_to_stream` / `recv_to_stream` / `RES_STREAM` op produced, optionally add one, push them back for a
+    following `copy_from_stream` / `send_from_stream` / `OP0_STREAM` op (reference
+    kernels/plugins/loopback, test/host/hls_simulator/test.cpp:153).  Returns the status tensor."""
+    if scratch is None:
+        scratch = accl.create_buffer(count, torch.float32)
+    status = torch.full((1,), -1, dtype=torch.int32, device=torch.device("cuda", accl.cuda_device))
+    _C.stream_loopback(accl.impl, scratch.impl, count, add_one, status.data_ptr(), _stream_handle(accl))
+    status._keep = scratch
+    return status

@@ -118,6 +118,21 @@ def build(with_cuda=True, verbose=False, force=False, tools=True):
     return out
 
 
+def build_sanitized(kind="address", verbose=False):
+    """CPU-only build of the emulator self-test under a sanitizer (`address` = ASan+UBSan,
+    `thread` = TSan): build/bin/emu_selftest_<kind>.  The reference configures none
+    (SURVEY 5.2); the emulator is the concurrent part of the host code (control thread, data
+    mover, fabric threads per rank), so this is where races and lifetime bugs would live."""
+    BIN.mkdir(parents=True, exist_ok=True)
+    flags = {"address": ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"],
+             "thread": ["-fsanitize=thread"]}[kind]
+    exe = BIN / f"emu_selftest_{kind}"
+    srcs = [str(CSRC / s) for s in HOST_SOURCES] + [str(CSRC / "tools" / "emu_selftest.cpp")]
+    _run([CXX, "-std=c++17", "-O1", "-g", *flags, "-I" + str(CSRC / "include"), *srcs, "-o", str(exe), "-lpthread"],
+         verbose)
+    return exe
+
+
 if __name__ == "__main__":
     import argparse
     ap = argparse.ArgumentParser()
@@ -125,5 +140,9 @@ if __name__ == "__main__":
     ap.add_argument("-v", "--verbose", action="store_true")
     ap.add_argument("-f", "--force", action="store_true")
     ap.add_argument("--no-tools", action="store_true")
+    ap.add_argument("--sanitize", choices=["address", "thread"], help="build build/bin/emu_selftest_<kind> only")
     a = ap.parse_args()
+    if a.sanitize:
+        print(build_sanitized(a.sanitize, a.verbose))
+        sys.exit(0)
     print(build(with_cuda=not a.cpu_only, verbose=a.verbose, force=a.force, tools=not a.no_tools))

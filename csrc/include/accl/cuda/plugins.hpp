@@ -34,5 +34,10 @@ cudaError_t launch_vadd_allreduce(CudaDevice &dev, uint64_t x_off, uint64_t y_of
                                   uint32_t count, uint32_t comm_adr, uint32_t dpcfg_adr, uint32_t *status_dev,
                                   cudaStream_t stream);
 
+// user kernel in the stream path: pulls `count` fp32 from this rank's stream FIFO, optionally adds one,
+// pushes them back (reference kernels/plugins/loopback).  scratch_off: heap scratch of count * 4 bytes.
+cudaError_t launch_loopback(CudaDevice &dev, uint64_t scratch_off, uint32_t count, bool add_one, uint32_t *status_dev,
+                            cudaStream_t stream);
+
 } // namespace cuda
 } // namespace accl

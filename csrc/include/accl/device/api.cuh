@@ -128,5 +128,116 @@ private:
   uint32_t comm_, dpcfg_, cflags_, sflags_;
 };
 
+// Data port of a user kernel: the rank's stream FIFO (reference ACCLData, accl_hls.h:455-541: push / pull
+// of 64-byte words on the streams between the user kernel and the CCLO).  The FIFO is a byte ring in the
+// symmetric heap; `push` may target a peer's ring (what `stream_put` lowers to).  All methods are
+// cooperative over ONE CTA (every thread of the block must call them with the same arguments).
+class Data {
+public:
+  __device__ explicit Data(const cuda::DevWorld &w) : w_(w) {}
+
+  // Wait for `bytes` in my FIFO and copy them to dst (any address space visible to the GPU).
+  // Returns 0 or KRNL_TIMEOUT_STS_ERROR.
+  __device__ uint32_t pull(void *dst, uint64_t bytes, uint64_t timeout_ns = 10ull * 1000 * 1000 * 1000) {
+    char *heap = w_.window + static_cast<uint64_t>(w_.rank) * w_.heap_bytes;
+    cuda::Ctrl *me = reinterpret_cast<cuda::Ctrl *>(heap);
+    __shared__ unsigned long long s_tail;
+    __shared__ int s_ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_tail = me->strm_tail;
+      s_ok = wait_ge(&me->strm_head, s_tail + bytes, timeout_ns) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_ok) return KRNL_TIMEOUT_STS_ERROR;
+    const char *fifo = heap + w_.strm_off;
+    char *d = static_cast<char *>(dst);
+    const unsigned long long tail = s_tail;
+    const uint64_t mask = w_.strm_cap - 1;
+    if (((tail | bytes | reinterpret_cast<uint64_t>(d)) & 15) == 0) {
+      for (uint64_t i = static_cast<uint64_t>(threadIdx.x) * 16; i < bytes; i += static_cast<uint64_t>(blockDim.x) * 16)
+        *reinterpret_cast<uint4 *>(d + i) = *reinterpret_cast<const uint4 *>(fifo + ((tail + i) & mask));
+    } else {
+      for (uint64_t i = threadIdx.x; i < bytes; i += blockDim.x) d[i] = fifo[(tail + i) & mask];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) dev::st_release_sys(&me->strm_tail, tail + bytes);
+    return 0;
+  }
+
+  // Append `bytes` from src to the FIFO of rank dst_rank (default: my own).  Producers on different GPUs
+  // reserve windows with a system-scope atomic and publish in reservation order.
+  __device__ uint32_t push(const void *src, uint64_t bytes, int dst_rank = -1, uint64_t timeout_ns = 10ull * 1000 * 1000 * 1000) {
+    const uint32_t dr = dst_rank < 0 ? w_.rank : static_cast<uint32_t>(dst_rank);
+    char *dheap = w_.window + static_cast<uint64_t>(dr) * w_.heap_bytes;
+    cuda::Ctrl *dc = reinterpret_cast<cuda::Ctrl *>(dheap);
+    __shared__ unsigned long long s_start;
+    __shared__ int s_ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long start;
+      asm volatile("atom.relaxed.sys.global.add.u64 %0, [%1], %2;"
+                   : "=l"(start) : "l"(&dc->strm_reserve), "l"(static_cast<unsigned long long>(bytes)) : "memory");
+      s_start = start;
+      s_ok = bytes <= w_.strm_cap;
+      uint32_t spins = 0;
+      uint64_t t0 = 0;
+      while (s_ok && start + bytes > dev::ld_acquire_sys(&dc->strm_tail) + w_.strm_cap) {
+        if (++spins > 16) dev::nanosleep(200);
+        if ((spins & 0xFF) == 0) {
+          const uint64_t now = dev::globaltimer_ns();
+          if (!t0) t0 = now;
+          else if (now - t0 > timeout_ns) s_ok = 0;
+        }
+      }
+    }
+    __syncthreads();
+    char *fifo = dheap + w_.strm_off;
+    const char *s = static_cast<const char *>(src);
+    const unsigned long long start = s_start;
+    const uint64_t mask = w_.strm_cap - 1;
+    const int ok = s_ok;
+    if (ok) {
+      if (((start | bytes | reinterpret_cast<uint64_t>(s)) & 15) == 0) {
+        for (uint64_t i = static_cast<uint64_t>(threadIdx.x) * 16; i < bytes; i += static_cast<uint64_t>(blockDim.x) * 16)
+          *reinterpret_cast<uint4 *>(fifo + ((start + i) & mask)) = *reinterpret_cast<const uint4 *>(s + i);
+      } else {
+        for (uint64_t i = threadIdx.x; i < bytes; i += blockDim.x) fifo[(start + i) & mask] = s[i];
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // publish in reservation order (even after a timeout, so later producers are not blocked forever)
+      wait_ge(&dc->strm_head, start, timeout_ns);
+      dev::st_release_sys(&dc->strm_head, start + bytes);
+    }
+    return ok ? 0u : static_cast<uint32_t>(KRNL_TIMEOUT_STS_ERROR);
+  }
+
+  // bytes currently readable in my FIFO (one thread)
+  __device__ uint64_t available() const {
+    const cuda::Ctrl *me = reinterpret_cast<const cuda::Ctrl *>(w_.window + static_cast<uint64_t>(w_.rank) * w_.heap_bytes);
+    return dev::ld_acquire_sys(&me->strm_head) - dev::ld_acquire_sys(&me->strm_tail);
+  }
+
+private:
+  static __device__ __forceinline__ bool wait_ge(const unsigned long long *p, unsigned long long target, uint64_t timeout_ns) {
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (dev::ld_acquire_sys(p) < target) {
+      if (++spins > 16) dev::nanosleep(200);
+      if ((spins & 0xFF) == 0) {
+        const uint64_t now = dev::globaltimer_ns();
+        if (!t0) t0 = now;
+        else if (now - t0 > timeout_ns) return false;
+      }
+    }
+    return true;
+  }
+  cuda::DevWorld w_;
+};
+
 } // namespace device
 } // namespace accl

@@ -54,6 +54,14 @@ void bind_cuda(py::module_ &m) {
                                           reinterpret_cast<uint32_t *>(status_dev_ptr), reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) throw std::runtime_error(std::string("vadd_allreduce launch: ") + cudaGetErrorString(e));
   }, py::call_guard<py::gil_scoped_release>());
+  m.def("stream_loopback", [](ACCL &a, BaseBuffer &scratch, uint32_t count, bool add_one, uintptr_t status_dev_ptr,
+                              uintptr_t stream) {
+    auto *d = dynamic_cast<CudaDevice *>(a.device());
+    if (!d) throw std::runtime_error("not a CUDA backend");
+    cudaError_t e = launch_loopback(*d, scratch.address(), count, add_one, reinterpret_cast<uint32_t *>(status_dev_ptr),
+                                    reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) throw std::runtime_error(std::string("stream_loopback launch: ") + cudaGetErrorString(e));
+  }, py::call_guard<py::gil_scoped_release>());
   m.def("cuda_probe", [](int device) { return probe_topology(device).describe(); });
   // N ranks in this process (threads), rank i on devices[i]
   m.def("make_cuda_world", [](std::vector<int> devices, size_t heap_mb, bool multicast, int max_ctas, bool engine,

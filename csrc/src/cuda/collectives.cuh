@@ -581,7 +581,9 @@ __device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_o
     case EP_SCATTER:
       if (me == root)
         for (uint32_t k = 0; k < P; ++k) {
-          const uint32_t q = (me + k) % P;
+          // CTAs visit the destinations in different orders: all P switch ports are fed at once
+          // instead of bursting one block at a time into a single port
+          const uint32_t q = (me + k + static_cast<uint32_t>(c.cta)) % P;
           copy_simple(c.heap(c.g(q)) + s_off2[q], src + q * blk, blk, c.cta, c.nctas);
         }
       break;
@@ -590,7 +592,7 @@ __device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_o
       break;
     case EP_ALLTOALL:
       for (uint32_t k = 0; k < P; ++k) {
-        const uint32_t q = (me + k) % P;
+        const uint32_t q = (me + k + static_cast<uint32_t>(c.cta)) % P;
         copy_simple(c.heap(c.g(q)) + s_off2[q] + me * blk, src + q * blk, blk, c.cta, c.nctas);
       }
       break;

@@ -39,6 +39,7 @@
 #include "accl/cuda/cudadevice.hpp"
 #include "accl/cuda/driver_api.hpp"
 #include "accl/cuda/plan.hpp"
+#include "accl/device/api.cuh"
 #include "run_work.cuh"
 
 namespace accl {
@@ -341,80 +342,21 @@ cudaError_t launch_reset_ctrl(const DevWorld &w, cudaStream_t stream) {
 
 
 // ---------------------------------------------------------------- stream port
-__device__ __forceinline__ bool strm_wait(const unsigned long long *p, unsigned long long target, uint64_t timeout_ns) {
-  uint32_t spins = 0;
-  uint64_t t0 = 0;
-  while (dev::ld_acquire_sys(p) < target) {
-    if (++spins > 16) dev::nanosleep(200);
-    if ((spins & 0xFF) == 0) {
-      const uint64_t now = dev::globaltimer_ns();
-      if (!t0) t0 = now;
-      else if (now - t0 > timeout_ns) return false;
-    }
-  }
-  return true;
-}
-
-// FIFO -> local buffer.  One CTA.
+// FIFO -> local buffer / local buffer -> FIFO of rank dst_rank (my own: RES_STREAM results; a peer's:
+// stream_put).  One CTA each; the bodies are the device API's Data port (accl/device/api.cuh).
 __global__ void __launch_bounds__(512) k_stream_pop(DevWorld w, uint64_t dst_off, uint64_t bytes, uint32_t timeout_us) {
   char *heap = w.window + static_cast<uint64_t>(w.rank) * w.heap_bytes;
-  Ctrl *me = reinterpret_cast<Ctrl *>(heap);
-  __shared__ unsigned long long s_tail;
-  __shared__ int s_ok;
-  if (threadIdx.x == 0) {
-    s_tail = me->strm_tail;
-    s_ok = strm_wait(&me->strm_head, s_tail + bytes, static_cast<uint64_t>(timeout_us) * 1000ull) ? 1 : 0;
-    if (!s_ok) atomicOr(&me->strm_err, static_cast<uint32_t>(KRNL_TIMEOUT_STS_ERROR));
-  }
-  __syncthreads();
-  if (!s_ok) return;
-  const char *fifo = heap + w.strm_off;
-  for (uint64_t i = threadIdx.x; i < bytes; i += blockDim.x) heap[dst_off + i] = fifo[(s_tail + i) & (w.strm_cap - 1)];
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) dev::st_release_sys(&me->strm_tail, s_tail + bytes);
+  device::Data port(w);
+  const uint32_t e = port.pull(heap + dst_off, bytes, static_cast<uint64_t>(timeout_us) * 1000ull);
+  if (e && threadIdx.x == 0) atomicOr(&reinterpret_cast<Ctrl *>(heap)->strm_err, e);
 }
 
-// local buffer -> FIFO of rank dst_rank (my own: RES_STREAM results; a peer's: stream_put).  One CTA.
 __global__ void __launch_bounds__(512) k_stream_push(DevWorld w, uint32_t dst_rank, uint64_t src_off, uint64_t bytes,
                                                      uint32_t timeout_us) {
   char *heap = w.window + static_cast<uint64_t>(w.rank) * w.heap_bytes;
-  Ctrl *me = reinterpret_cast<Ctrl *>(heap);
-  char *dheap = w.window + static_cast<uint64_t>(dst_rank) * w.heap_bytes;
-  Ctrl *dc = reinterpret_cast<Ctrl *>(dheap);
-  __shared__ unsigned long long s_start;
-  __shared__ int s_ok;
-  const uint64_t tmo = static_cast<uint64_t>(timeout_us) * 1000ull;
-  if (threadIdx.x == 0) {
-    // reserve a window (system-scope atomic: producers may sit on different GPUs), then wait for room
-    unsigned long long start;
-    asm volatile("atom.relaxed.sys.global.add.u64 %0, [%1], %2;" : "=l"(start) : "l"(&dc->strm_reserve), "l"(static_cast<unsigned long long>(bytes)) : "memory");
-    s_start = start;
-    s_ok = 1;
-    if (bytes > w.strm_cap) s_ok = 0;
-    uint32_t spins = 0;
-    uint64_t t0 = 0;
-    while (s_ok && start + bytes > dev::ld_acquire_sys(&dc->strm_tail) + w.strm_cap) {
-      if (++spins > 16) dev::nanosleep(200);
-      if ((spins & 0xFF) == 0) {
-        const uint64_t now = dev::globaltimer_ns();
-        if (!t0) t0 = now;
-        else if (now - t0 > tmo) s_ok = 0;
-      }
-    }
-    if (!s_ok) atomicOr(&me->strm_err, static_cast<uint32_t>(KRNL_TIMEOUT_STS_ERROR));
-  }
-  __syncthreads();
-  char *fifo = dheap + w.strm_off;
-  if (s_ok)
-    for (uint64_t i = threadIdx.x; i < bytes; i += blockDim.x) fifo[(s_start + i) & (w.strm_cap - 1)] = heap[src_off + i];
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // publish in reservation order (even after a timeout, so later producers are not blocked forever)
-    strm_wait(&dc->strm_head, s_start, tmo);
-    dev::st_release_sys(&dc->strm_head, s_start + bytes);
-  }
+  device::Data port(w);
+  const uint32_t e = port.push(heap + src_off, bytes, static_cast<int>(dst_rank), static_cast<uint64_t>(timeout_us) * 1000ull);
+  if (e && threadIdx.x == 0) atomicOr(&reinterpret_cast<Ctrl *>(heap)->strm_err, e);
 }
 
 cudaError_t launch_stream_pop(const DevWorld &w, uint64_t dst_off, uint64_t bytes, uint32_t timeout_us, cudaStream_t stream) {

@@ -38,9 +38,35 @@ __global__ void __launch_bounds__(512) k_plugin_vadd_allreduce(DevWorld w, uint6
   }
 }
 
+// The reference's `loopback` user kernel (kernels/plugins/loopback/loopback.cpp): consume words from the
+// engine->kernel stream and hand them back on the kernel->engine stream, here with an optional +1 so a
+// test can tell the data really went through the kernel.  One CTA; `Data` is the device API's stream port.
+__global__ void __launch_bounds__(256) k_plugin_loopback(DevWorld w, uint64_t scratch_off, uint32_t count, int add_one,
+                                                         uint32_t *status) {
+  char *heap = w.window + static_cast<uint64_t>(w.rank) * w.heap_bytes;
+  float *tmp = reinterpret_cast<float *>(heap + scratch_off);
+  device::Data port(w);
+  uint32_t e = port.pull(tmp, static_cast<uint64_t>(count) * 4);
+  if (!e) {
+    if (add_one)
+      for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) tmp[i] += 1.0f;
+    __syncthreads();
+    e = port.push(tmp, static_cast<uint64_t>(count) * 4);
+  }
+  if (threadIdx.x == 0 && status) *status = e;
+}
+
 void preload_vadd_kernels() {
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, k_plugin_vadd_allreduce);
+  cudaFuncGetAttributes(&a, k_plugin_loopback);
+}
+
+cudaError_t launch_loopback(CudaDevice &dev, uint64_t scratch_off, uint32_t count, bool add_one, uint32_t *status_dev,
+                            cudaStream_t stream) {
+  ACCL_CUDART(cudaSetDevice(dev.device()));
+  k_plugin_loopback<<<1, 256, 0, stream>>>(dev.world(), scratch_off, count, add_one ? 1 : 0, status_dev);
+  return cudaGetLastError();
 }
 
 static void CUDART_CB unpin_cb(void *user) { static_cast<Engine *>(user)->unpin(); }

@@ -371,3 +371,26 @@ def test_large_bcast_is_pipelined_over_workers():
             a.bcast(b, n, root)
             assert torch.equal(b.host, data(n, root, salt=root))
     A.run_cuda_ranks(devices(3), fn, RNDZV, heap_mb=512, max_ctas=8)
+
+
+@pytest.mark.parametrize("cfg", PROTOCOLS)
+def test_stress_sendrecv_ring(cfg):
+    """2000 tagged exchanges around a ring without re-initialising (reference stress.cpp:24-33):
+    slot credits, sequence numbers and sync pads must survive wrap-around of the small rings."""
+    iters = 2000
+
+    def fn(a, r, w):
+        s, d = a.create_buffer(COUNT), a.create_buffer(COUNT)
+        nxt, prv = (r + 1) % w, (r - 1) % w
+        for i in range(iters):
+            s.dev.fill_(float(r * 10000 + i))
+            if r % 2 == 0:
+                a.send(s, COUNT, nxt, tag=i & 0xFF, from_fpga=True)
+                a.recv(d, COUNT, prv, tag=i & 0xFF, to_fpga=True)
+            else:
+                a.recv(d, COUNT, prv, tag=i & 0xFF, to_fpga=True)
+                a.send(s, COUNT, nxt, tag=i & 0xFF, from_fpga=True)
+            if i % 250 == 0 or i == iters - 1:
+                torch.cuda.synchronize()
+                assert float(d.dev[0]) == float(prv * 10000 + i) and float(d.dev[-1]) == float(prv * 10000 + i)
+    run(2, fn, cfg)

@@ -111,3 +111,30 @@ def test_tensor_group_and_row_parallel_linear():
     rows = full.shape[0] // 2
     for r, (y, _, _) in enumerate(res):
         assert close(y, full[r * rows:(r + 1) * rows], 2e-2, 3e-1)
+
+
+def test_user_kernel_in_the_stream_path():
+    """send -> recv_to_stream -> user kernel (device::Data pull / +1 / push) -> send_from_stream -> recv
+    (reference test/host/hls_simulator/test.cpp:153 `test_loopback`)."""
+    from accl_b200 import DataType
+    from accl_b200.ops import stream_loopback
+    n = 2048
+
+    def fn(a, r, w):
+        s, d = a.create_buffer(n), a.create_buffer(n)
+        s.host[:] = torch.arange(n, dtype=torch.float32) + 100 * r
+        nxt, prv = (r + 1) % w, (r - 1) % w
+        req = a.send(s, n, nxt, tag=3, run_async=True)
+        a.recv_to_stream(DataType.float32, n, prv, tag=3)
+        req.wait()
+        st = stream_loopback(a, n, add_one=True)
+        req = a.send_from_stream(DataType.float32, n, nxt, tag=4, run_async=True)
+        a.recv(d, n, prv, tag=4)
+        req.wait()
+        torch.cuda.synchronize()
+        assert int(st.item()) == 0
+        # data made two hops: it comes from the rank two places behind me, plus one
+        src = (r - 2) % w
+        assert torch.equal(d.host, torch.arange(n, dtype=torch.float32) + 100 * src + 1)
+    A.run_cuda_ranks(devices(2), fn, dict(n_egr_rx_bufs=4, egr_rx_buf_size=16 << 10, max_egr_size=16 << 10,
+                                          max_rndzv_size=1 << 26), heap_mb=64, max_ctas=4)

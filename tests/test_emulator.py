@@ -582,3 +582,25 @@ def test_device_issued_call_through_second_port():
         d.sync_from_device()
         assert torch.equal(s.host, d.host)
     A.run_ranks(1, fn)
+
+
+# ------------------------------------------------------------ stress (reference test/host/xrt/src/stress.cpp:24-33)
+@pytest.mark.parametrize("cfg", PROTOCOLS)
+def test_stress_sendrecv_ring(cfg):
+    iters = 400
+
+    def fn(a, r, w):
+        s, d = a.create_buffer(COUNT), a.create_buffer(COUNT)
+        nxt, prv = (r + 1) % w, (r - 1) % w
+        for i in range(iters):
+            s.host[:] = data(COUNT, r, salt=i & 7)
+            if r % 2 == 0:
+                a.send(s, COUNT, nxt, tag=i & 0xFF)
+                a.recv(d, COUNT, prv, tag=i & 0xFF)
+            else:
+                a.recv(d, COUNT, prv, tag=i & 0xFF)
+                a.send(s, COUNT, nxt, tag=i & 0xFF)
+            if i % 50 == 0:
+                assert torch.equal(d.host, data(COUNT, prv, salt=i & 7))
+        assert torch.equal(d.host, data(COUNT, prv, salt=(iters - 1) & 7))
+    A.run_ranks(4, fn, cfg)
