@@ -27,8 +27,8 @@ _C = _load_native()
 sys.modules.setdefault("accl_b200._C", _C)
 
 from .core import (Accl, Buffer, BufferKind, DataType, GLOBAL_COMM, MAX, ReduceFunction, SUM, TAG_ANY,  # noqa: E402
-                   cuda_rank, cuda_world, emulator_world, run_cuda_ranks, run_ranks, socket_rank)
+                   cuda_rank, cuda_world, emulator_world, remote_rank, run_cuda_ranks, run_ranks, socket_rank)
 
 __all__ = ["Accl", "Buffer", "BufferKind", "DataType", "GLOBAL_COMM", "MAX", "ReduceFunction", "SUM", "TAG_ANY",
-           "emulator_world", "run_ranks", "socket_rank", "cuda_world", "cuda_rank", "run_cuda_ranks", "_C"]
+           "emulator_world", "run_ranks", "socket_rank", "remote_rank", "cuda_world", "cuda_rank", "run_cuda_ranks", "_C"]
 __version__ = "0.1.0"

@@ -371,6 +371,16 @@ def socket_rank(rank=None, world_size=None, addr="127.0.0.1", base_port=None, me
     return Accl(_C.make_emu_socket(rank, world_size, addr, base_port, mem_mb), rank, world_size)
 
 
+def remote_rank(rank=None, world_size=None, addr="127.0.0.1", ctrl_port=None, connect_timeout_s=60):
+    """Driver for a stand-alone engine process (`build/bin/cclo_emu`, see
+    accl_b200.models.emulator.spawn_engines): the reference's SimDevice <-> cclo_emu split."""
+    rank = int(os.environ.get("RANK", 0)) if rank is None else rank
+    world_size = int(os.environ.get("WORLD_SIZE", 1)) if world_size is None else world_size
+    if ctrl_port is None:
+        ctrl_port = int(os.environ.get("ACCL_EMU_PORT", 5500)) + 1000 + rank
+    return Accl(_C.make_emu_remote(rank, world_size, addr, ctrl_port, connect_timeout_s), rank, world_size)
+
+
 # --------------------------------------------------------------------- CUDA
 def _prepare_cuda_env():
     # ranks sharing one process/GPU need independent hardware queues, or one

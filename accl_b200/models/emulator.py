@@ -4,6 +4,9 @@ talking over loopback TCP (SocketFabric).
   python -m accl_b200.models.emulator -n 4 --selftest          # spawn + run the built-in check
   python -m accl_b200.models.emulator -n 4 -- python my_app.py # spawn an app once per rank
 
+  python -m accl_b200.models.emulator -n 4 --engines           # only the engine processes (cclo_emu); drivers
+                                                               # attach with accl_b200.remote_rank()
+
 Every child gets RANK / WORLD_SIZE / ACCL_EMU_PORT; inside, `accl_b200.socket_rank()`
 gives the rank's Accl.  Counterpart of the reference's test/model/emulator/run.py
 (spawns N cclo_emu processes) + utility.cpp `--startemu`; signal handling tears
@@ -69,6 +72,33 @@ def launch(world, argv, base_port=None, env_extra=None, timeout=None):
         kill_all()
 
 
+def engine_binary():
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    exe = os.path.join(root, "build", "bin", "cclo_emu")
+    if not os.path.exists(exe):
+        from ..utils import build as _b
+        _b.build_tool("cclo_emu")
+    return exe
+
+
+def spawn_engines(world, base_port=None, mem_mb=64, loopback=True, log_level=None, stderr=None):
+    """Start one stand-alone engine process per rank (reference run.py: N x cclo_emu).  Rank r's engine
+    listens for the other engines on base_port + r and for its driver on base_port + 1000 + r.
+    Returns (procs, base_port); attach with `accl_b200.remote_rank(r, world, ctrl_port=base_port + 1000 + r)`."""
+    base_port = base_port or free_port_block(world)
+    exe = engine_binary()
+    procs = []
+    for r in range(world):
+        cmd = [exe, "--rank", str(r), "--world", str(world), "--base-port", str(base_port), "--ctrl-port",
+               str(base_port + 1000 + r), "--mem-mb", str(mem_mb)]
+        if not loopback:
+            cmd.append("--no-kernel-loopback")
+        if log_level is not None:
+            cmd += ["--log-level", str(log_level)]
+        procs.append(subprocess.Popen(cmd, stderr=stderr))
+    return procs, base_port
+
+
 def selftest():
     """What each rank runs under --selftest: BASELINE config #1 (send/recv + allreduce fp32)."""
     import torch
@@ -98,12 +128,23 @@ def main():
     ap.add_argument("-n", "--nranks", type=int, default=2)
     ap.add_argument("-p", "--port", type=int, default=0, help="base port (rank r listens on port + r); 0 = pick")
     ap.add_argument("--selftest", action="store_true")
+    ap.add_argument("--engines", action="store_true", help="run only the cclo_emu engine processes until interrupted")
     ap.add_argument("--child-selftest", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("cmd", nargs=argparse.REMAINDER)
     a = ap.parse_args()
     if a.child_selftest:
         selftest()
         return 0
+    if a.engines:
+        procs, base = spawn_engines(a.nranks, a.port or None)
+        print(f"engines up: fabric ports {base}..{base + a.nranks - 1}, control ports {base + 1000}..{base + 1000 + a.nranks - 1}",
+              flush=True)
+        try:
+            return max(p.wait() for p in procs)
+        except KeyboardInterrupt:
+            for p in procs:
+                p.terminate()
+            return 130
     argv = [sys.executable, "-m", "accl_b200.models.emulator", "--child-selftest"] if a.selftest else [c for c in a.cmd if c != "--"]
     if not argv:
         ap.error("nothing to run: pass --selftest or a command after --")

@@ -29,7 +29,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 HOST_SOURCES = [
     "src/host/accl.cpp", "src/host/arithconfig.cpp", "src/host/bootstrap.cpp", "src/host/common.cpp",
     "src/host/communicator.cpp", "src/host/constants.cpp",
-    "src/emu/engine.cpp", "src/emu/firmware.cpp", "src/emu/fabric.cpp", "src/emu/emudevice.cpp",
+    "src/emu/engine.cpp", "src/emu/firmware.cpp", "src/emu/fabric.cpp", "src/emu/emudevice.cpp", "src/emu/remote.cpp",
 ]
 CUDA_HOST_SOURCES = ["src/cuda/driver_api.cpp", "src/cuda/symheap.cpp"]
 CUDA_SOURCES = []  # filled below from csrc/src/cuda/*.cu
@@ -105,6 +105,9 @@ def build(with_cuda=True, verbose=False, force=False, tools=True):
         else:
             link = [CXX, "-shared", "-fPIC", *[str(o) for o in objs], "-o", str(out), "-lpthread"]
         _run(link, verbose)
+    if tools and not with_cuda:
+        for name in ("cclo_emu", "emu_selftest"):
+            build_tool(name, verbose)
     if tools and with_cuda:
         lib_objs = [o for o, s in zip(objs, srcs) if s != BINDING and "bind_" not in s]
         for tool in sorted((CSRC / "tools").glob("*.cu")) + sorted((CSRC / "tools").glob("*.cpp")):
@@ -116,6 +119,15 @@ def build(with_cuda=True, verbose=False, force=False, tools=True):
                   "-I" + str(CSRC / "include"), str(tool), *[str(o) for o in lib_objs], "-o", str(exe),
                   "-lpthread", "-ldl", "-lrt"], verbose)
     return out
+
+
+def build_tool(name, verbose=False):
+    """Host-only tools (cclo_emu, emu_selftest) need no CUDA toolchain: g++ build into build/bin."""
+    BIN.mkdir(parents=True, exist_ok=True)
+    exe = BIN / name
+    srcs = [str(CSRC / s) for s in HOST_SOURCES] + [str(CSRC / "tools" / (name + ".cpp"))]
+    _run([CXX, "-std=c++17", "-O2", "-g1", "-I" + str(CSRC / "include"), *srcs, "-o", str(exe), "-lpthread"], verbose)
+    return exe
 
 
 def build_sanitized(kind="address", verbose=False):

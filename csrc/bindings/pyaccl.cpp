@@ -19,6 +19,7 @@
 #include "accl/accl.hpp"
 #include "accl/bootstrap.hpp"
 #include "accl/emu/emudevice.hpp"
+#include "accl/emu/remote.hpp"
 #include "accl/emu/softfloat.hpp"
 #include "accl/exchmem.hpp"
 #ifdef ACCL_WITH_CUDA
@@ -259,24 +260,34 @@ PYBIND11_MODULE(_C, m) {
       .def_property_readonly("max_rendezvous_size", &ACCL::max_rendezvous_size)
       // ---- emulator-only: device-side stream ports (the BFM of the reference)
       .def("emu_kernel_push", [](ACCL &a, py::bytes data) {
+        std::string s = data;
+        if (auto *rd = dynamic_cast<emu::RemoteDevice *>(a.device())) {
+          py::gil_scoped_release rel;
+          rd->kernel_push(s.data(), s.size());
+          return;
+        }
         auto *d = dynamic_cast<emu::EmuDevice *>(a.device());
         if (!d) throw std::runtime_error("not an emulator backend");
-        std::string s = data;
         d->engine().kernel_push(s.data(), s.size());
       })
       .def("emu_kernel_pull", [](ACCL &a, unsigned strm, size_t bytes, int timeout_ms) {
         auto *d = dynamic_cast<emu::EmuDevice *>(a.device());
-        if (!d) throw std::runtime_error("not an emulator backend");
+        auto *rd = dynamic_cast<emu::RemoteDevice *>(a.device());
+        if (!d && !rd) throw std::runtime_error("not an emulator backend");
         std::string out(bytes, '\0');
         bool ok;
         {
           py::gil_scoped_release rel;
-          ok = d->engine().kernel_pull(strm, &out[0], bytes, timeout_ms);
+          ok = rd ? rd->kernel_pull(strm, &out[0], bytes, timeout_ms) : d->engine().kernel_pull(strm, &out[0], bytes, timeout_ms);
         }
         if (!ok) throw std::runtime_error("emu_kernel_pull: timed out");
         return py::bytes(out);
       }, py::arg("stream_id"), py::arg("nbytes"), py::arg("timeout_ms") = 5000)
       .def("emu_set_kernel_loopback", [](ACCL &a, bool on) {
+        if (auto *rd = dynamic_cast<emu::RemoteDevice *>(a.device())) {
+          rd->set_kernel_loopback(on);
+          return;
+        }
         auto *d = dynamic_cast<emu::EmuDevice *>(a.device());
         if (!d) throw std::runtime_error("not an emulator backend");
         d->engine().set_kernel_loopback(on);
@@ -309,6 +320,23 @@ PYBIND11_MODULE(_C, m) {
     return std::unique_ptr<ACCL>(new ACCL(std::unique_ptr<CCLO>(new emu::EmuDevice(fabric, rank, world, mem_mb << 20))));
   }, py::arg("rank"), py::arg("world_size"), py::arg("addr") = "127.0.0.1", py::arg("base_port") = 5500,
         py::arg("mem_mb") = 256, gil_release());
+
+  // driver side of a stand-alone engine process (build/bin/cclo_emu) listening on addr:ctrl_port
+  m.def("make_emu_remote", [](int rank, int world, const std::string &addr, int ctrl_port, int connect_timeout_s) {
+    return std::unique_ptr<ACCL>(
+        new ACCL(std::unique_ptr<CCLO>(new emu::RemoteDevice(addr, ctrl_port, rank, world, connect_timeout_s))));
+  }, py::arg("rank"), py::arg("world_size"), py::arg("addr") = "127.0.0.1", py::arg("ctrl_port") = 6500,
+        py::arg("connect_timeout_s") = 60, gil_release());
+  m.def("emu_remote_shutdown", [](ACCL &a) {
+    auto *rd = dynamic_cast<emu::RemoteDevice *>(a.device());
+    if (!rd) throw std::runtime_error("not a remote emulator backend");
+    rd->shutdown_engine();
+  }, gil_release());
+  m.def("emu_remote_debug_state", [](ACCL &a) {
+    auto *rd = dynamic_cast<emu::RemoteDevice *>(a.device());
+    if (!rd) throw std::runtime_error("not a remote emulator backend");
+    return rd->debug_state();
+  }, gil_release());
 
   // ---- numerics helpers used by tests as the reference for narrow floats
   m.def("encode_float", [](float f, dataType t) -> uint32_t {

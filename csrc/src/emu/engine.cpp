@@ -189,14 +189,16 @@ void Engine::control_loop() {
     write_exch(exchmem::RETCODE, rc);
     write_exch(exchmem::PERFCNT_LO, static_cast<uint32_t>(dur));
     write_exch(exchmem::PERFCNT_HI, static_cast<uint32_t>(dur >> 32));
+    if (c.req) c.req->complete(rc, dur); // first: completion hooks may read the request's outcome
     if (c.on_done) c.on_done(rc);
-    if (c.req) c.req->complete(rc, dur);
   }
   // fail whatever is still queued so waiters wake up
   std::lock_guard<std::mutex> g(q_m_);
   for (auto *q : {&new_calls_, &retry_calls_})
-    for (auto &c : *q)
+    for (auto &c : *q) {
       if (c.req) c.req->complete(NOT_READY_ERROR, 0);
+      if (c.on_done) c.on_done(NOT_READY_ERROR);
+    }
 }
 
 void Engine::soft_reset() {
@@ -208,8 +210,8 @@ void Engine::soft_reset() {
     done_notes_.clear();
   }
   for (auto &c : parked) {
-    if (c.on_done) c.on_done(NOT_READY_ERROR);
     if (c.req) c.req->complete(NOT_READY_ERROR, 0);
+    if (c.on_done) c.on_done(NOT_READY_ERROR);
   }
   {
     std::lock_guard<std::mutex> g(rx_m_);

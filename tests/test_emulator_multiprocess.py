@@ -16,3 +16,64 @@ def test_selftest_over_sockets(world):
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count(": ok") == world
+
+
+def test_standalone_engine_processes_with_remote_drivers():
+    """Engines as separate processes (build/bin/cclo_emu), drivers attach over the control socket:
+    the reference's cclo_emu + SimDevice deployment (test/model/emulator/run.py, simdevice.cpp)."""
+    import threading
+
+    import torch
+
+    import accl_b200 as A
+    from accl_b200.models.emulator import spawn_engines
+
+    world = 3
+    procs, base = spawn_engines(world, mem_mb=32, stderr=subprocess.DEVNULL)
+    errors = []
+
+    def driver(r):
+        try:
+            a = A.remote_rank(r, world, ctrl_port=base + 1000 + r)
+            assert "RemoteDevice" in a.describe()
+            a.initialize(n_egr_rx_bufs=16, egr_rx_buf_size=1024, max_egr_size=1024, max_rndzv_size=32768)
+            for n in (16, 300, 20000):  # eager, segmented eager, rendezvous
+                s, d = a.create_buffer(n), a.create_buffer(n)
+                s.host[:] = torch.arange(n, dtype=torch.float32) + r
+                nxt, prv = (r + 1) % world, (r - 1) % world
+                req = a.send(s, n, nxt, tag=3, run_async=True)
+                a.recv(d, n, prv, tag=3)
+                req.wait()
+                assert torch.equal(d.host, torch.arange(n, dtype=torch.float32) + prv)
+                req = a.allreduce(s, d, n, A.SUM, run_async=True)
+                req.wait()
+                d.sync_from_device()  # async call with a host-resident result: the read-back is ours
+                assert req.duration_ns() > 0
+                ref = sum(torch.arange(n, dtype=torch.float32) + q for q in range(world))
+                assert torch.allclose(d.host, ref)
+            # stream port through the control connection (kernel loopback is on by default)
+            s, d = a.create_buffer(64), a.create_buffer(64)
+            s.host[:] = torch.arange(64, dtype=torch.float32) * (r + 1)
+            a.copy_to_stream(s, 64)
+            a.copy_from_stream(d, 64)
+            assert torch.equal(s.host, d.host)
+            a.barrier()
+            a.deinit()
+            A._C.emu_remote_shutdown(a.impl)
+        except BaseException as e:  # noqa: BLE001
+            errors.append((r, repr(e)))
+
+    ts = [threading.Thread(target=driver, args=(r,)) for r in range(world)]
+    try:
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(timeout=120)
+        assert not errors, errors
+        assert all(not t.is_alive() for t in ts), "driver hung"
+        for p in procs:
+            assert p.wait(timeout=30) == 0
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
