@@ -56,6 +56,14 @@ class TensorGroup:
         self.rank = accl.get_comm_rank(comm_id)
         self._scratch = {}
         self._scratch_bytes = scratch_bytes
+        # CUDA: operands are device resident and calls are stream ordered.  Emulator: the tensor side of a
+        # buffer is its host mirror, so calls are blocking and sync to / from the engine's memory themselves.
+        self._res = bool(accl.is_cuda)
+        self._async = bool(accl.is_cuda)
+
+    def _t(self, buf):
+        """The torch tensor aliasing a buffer on this backend."""
+        return buf.dev if self._res else buf.host
 
     # -- heap-resident tensors -------------------------------------------
     def empty(self, *shape, dtype=torch.float32):
@@ -64,7 +72,7 @@ class TensorGroup:
         for s in shape:
             n *= s
         buf = self.accl.create_buffer(n, dtype)
-        t = buf.dev.view(*shape)
+        t = self._t(buf).view(*shape)
         t._accl_buffer = buf
         return t
 
@@ -82,44 +90,45 @@ class TensorGroup:
         sb, s_staged = self._buffer_of(src, "s")
         db, d_staged = (sb, s_staged) if dst is src else self._buffer_of(dst, "d")
         if s_staged:
-            sb.dev[:src.numel()].copy_(src.reshape(-1))
+            self._t(sb)[:src.numel()].copy_(src.reshape(-1))
         req = fn(sb, db)
         if d_staged:
-            dst.reshape(-1).copy_(db.dev[:dst.numel()])
+            dst.reshape(-1).copy_(self._t(db)[:dst.numel()])
         return req
 
     # -- collectives ---------------------------------------------------------
     def all_reduce(self, t: torch.Tensor, op=SUM):
         n = t.numel()
-        return self._run(lambda s, d: self.accl.allreduce(s, d, n, op, self.comm_id, True, True, run_async=True), t, t, n, n)
+        return self._run(lambda s, d: self.accl.allreduce(s, d, n, op, self.comm_id, self._res, self._res, run_async=self._async), t, t, n, n)
 
     def broadcast(self, t: torch.Tensor, root=0):
         n = t.numel()
-        return self._run(lambda s, d: self.accl.bcast(s, n, root, self.comm_id, True, True, run_async=True), t, t, n, n)
+        return self._run(lambda s, d: self.accl.bcast(s, n, root, self.comm_id, self._res, self._res, run_async=self._async), t, t, n, n)
 
     def all_gather_into_tensor(self, out: torch.Tensor, inp: torch.Tensor):
         n = inp.numel()
-        return self._run(lambda s, d: self.accl.allgather(s, d, n, self.comm_id, True, True, run_async=True), inp, out, n, n * self.world)
+        return self._run(lambda s, d: self.accl.allgather(s, d, n, self.comm_id, self._res, self._res, run_async=self._async), inp, out, n, n * self.world)
 
     def reduce_scatter_tensor(self, out: torch.Tensor, inp: torch.Tensor, op=SUM):
         n = out.numel()
-        return self._run(lambda s, d: self.accl.reduce_scatter(s, d, n, op, self.comm_id, True, True, run_async=True), inp, out, n * self.world, n)
+        return self._run(lambda s, d: self.accl.reduce_scatter(s, d, n, op, self.comm_id, self._res, self._res, run_async=self._async), inp, out, n * self.world, n)
 
     def all_to_all_single(self, out: torch.Tensor, inp: torch.Tensor):
         n = inp.numel() // self.world
-        return self._run(lambda s, d: self.accl.alltoall(s, d, n, self.comm_id, True, True, run_async=True), inp, out, n * self.world, n * self.world)
+        return self._run(lambda s, d: self.accl.alltoall(s, d, n, self.comm_id, self._res, self._res, run_async=self._async), inp, out, n * self.world, n * self.world)
 
     def send(self, t: torch.Tensor, dst, tag=0):
         sb, staged = self._buffer_of(t, "s")
         if staged:
-            sb.dev[:t.numel()].copy_(t.reshape(-1))
-        return self.accl.send(sb, t.numel(), dst, tag, self.comm_id, True, run_async=True)
+            self._t(sb)[:t.numel()].copy_(t.reshape(-1))
+        # always asynchronous: a blocking rendezvous send would wait for the peer's recv
+        return self.accl.send(sb, t.numel(), dst, tag, self.comm_id, self._res, run_async=True)
 
     def recv(self, t: torch.Tensor, src, tag=0):
         db, staged = self._buffer_of(t, "d")
-        req = self.accl.recv(db, t.numel(), src, tag, self.comm_id, True, run_async=True)
+        req = self.accl.recv(db, t.numel(), src, tag, self.comm_id, self._res, run_async=self._async)
         if staged:
-            t.reshape(-1).copy_(db.dev[:t.numel()])
+            t.reshape(-1).copy_(self._t(db)[:t.numel()])
         return req
 
     def barrier(self):
@@ -157,7 +166,8 @@ class GradBucket:
         buf = self.flat._accl_buffer
         n = self.numel // self.group.world
         out = self.group.empty(n, dtype=self.flat.dtype)
-        self.group.accl.reduce_scatter(buf, out._accl_buffer, n, SUM, self.group.comm_id, True, True, run_async=True)
+        g = self.group
+        g.accl.reduce_scatter(buf, out._accl_buffer, n, SUM, g.comm_id, g._res, g._res, run_async=g._async)
         del shard
         return out
 
