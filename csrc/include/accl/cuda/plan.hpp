@@ -78,7 +78,12 @@ ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
   // one-shot (everybody pulls everything) moves P x the bytes of two-shot: only while latency dominates
   if (op == operation::allreduce && ubytes * P <= cfg.oneshot_max_bytes) w.algo = ALGO_P2P_ONESHOT;
   if (op == operation::send || op == operation::recv) w.algo = ALGO_P2P;
-  w.n_ctas = plan_ctas(moved, 128u << 10, cap);
+  uint32_t c = cap;
+  // measured on 8 x B200 (profiles/sweep_8gpu_{nvls,p2p}*.csv, 64 vs 128 CTAs): two-shot all-reduce is
+  // 5-25 % faster with 64 channels through the switch at every size and up to 128 MiB over peer loads /
+  // stores (fewer flag round trips per byte); the other collectives do not care
+  if (op == operation::allreduce && (w.algo == ALGO_NVLS || ubytes <= (128ull << 20)) && c > 64) c = 64;
+  w.n_ctas = plan_ctas(moved, 128u << 10, c);
 }
 
 // Decode + plan.  Returns an error word (0 = ok).
