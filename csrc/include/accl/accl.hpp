@@ -136,7 +136,7 @@ public:
   bool test(ACCLRequest *request) { return cclo->test(request); }
   uint64_t get_duration(ACCLRequest *request) { return cclo->get_duration(request); }
   val_t get_retcode(ACCLRequest *request) { return cclo->get_retcode(request); }
-  void free_request(ACCLRequest *request) { cclo->free_request(request); }
+  void free_request(ACCLRequest *request);
 
   // ---- communicators
   std::vector<rank_t> get_comm_group(communicatorId comm_id);
@@ -211,6 +211,7 @@ private:
   addr_t max_eager_size_ = 0, max_rndzv_size_ = 0, eager_rx_buf_size_ = 0;
   bool config_rdy = false;
   void *stream_ = nullptr;
+  int trace_rank_ = 0; // pid of this instance's events in ACCL_TRACE output
 };
 
 } // namespace accl

@@ -14,6 +14,7 @@
 #include <mutex>
 #include <sstream>
 #include <string>
+#include <vector>
 
 #if defined(__CUDACC__)
 #define ACCL_HD __host__ __device__ __forceinline__
@@ -78,6 +79,44 @@ private:
   using clock = std::chrono::steady_clock;
   clock::time_point t0_, t1_;
   bool running_ = false;
+};
+
+// Per-call tracing.  ACCL_TRACE=<prefix> writes <prefix><rank>.json in Chrome / Perfetto
+// trace-event format when the process exits (or on flush()): one complete event per call with the host
+// issue time as timestamp and the ENGINE-measured duration (perf counter / %globaltimer) as length, plus
+// count, communicator, return code and the host-side issue cost.  ACCL_NVTX=1 additionally brackets every
+// call issue in an NVTX range (CUDA builds) so that nsys / ncu timelines show the collective names.
+class Tracer {
+public:
+  static Tracer &get();
+  static bool enabled() { return enabled_; }
+  static bool nvtx() { return nvtx_; }
+  // key identifies the request until complete() is called for it
+  void issue(const void *key, int rank, const char *op, unsigned count, unsigned comm, uint64_t issue_cost_ns);
+  void complete(const void *key, uint32_t retcode, uint64_t device_ns);
+  void flush();
+  uint64_t now_ns() const;
+  void range_push(const char *name);
+  void range_pop();
+
+private:
+  Tracer();
+  ~Tracer();
+  struct Ev {
+    const char *op;
+    int rank;
+    unsigned count, comm;
+    uint64_t t_issue_ns, issue_cost_ns, device_ns;
+    uint32_t retcode;
+    bool done;
+  };
+  static bool enabled_, nvtx_;
+  std::mutex m_;
+  std::string path_;
+  std::vector<Ev> events_;
+  std::vector<std::pair<const void *, size_t>> open_; // request key -> index into events_
+  std::chrono::steady_clock::time_point t0_;
+  int rank_ = 0;
 };
 
 // dotted-quad <-> u32, kept for rank tables that carry addresses

@@ -80,6 +80,7 @@ void ACCL::initialize(const std::vector<rank_t> &ranks, int local_rank, int n_eg
     throw std::invalid_argument("initialize: bad rank table / local rank");
   if (ranks.size() > static_cast<size_t>(ACCL_MAX_RANKS))
     throw std::invalid_argument("initialize: more than ACCL_MAX_RANKS ranks");
+  trace_rank_ = local_rank;
   cclo->attach(static_cast<int>(ranks.size()), ranks[static_cast<size_t>(local_rank)].session_id);
   parse_hwid();
   if (cclo->read(exchmem::CFGRDY) != 0)
@@ -244,7 +245,7 @@ void ACCL::check_return_value(const std::string &fn, ACCLRequest *request) {
     std::string msg = "CCLO @" + fn + ": " + error_word_to_string(rc) + " (0x";
     std::ostringstream h;
     h << std::hex << rc;
-    cclo->free_request(request);
+    free_request(request);
     throw std::runtime_error(msg + h.str() + ")");
   }
 }
@@ -299,18 +300,46 @@ void ACCL::prepare_call(CCLO::Options &o) {
   o.arithcfg_addr = cfg->exchmem_addr;
 }
 
+namespace {
+// tracing hooks around the backend's start / call (no cost unless ACCL_TRACE / ACCL_NVTX are set)
+template <typename F> ACCLRequest *traced(const CCLO::Options &o, int rank, F &&issue) {
+  Tracer &t = Tracer::get();
+  if (!Tracer::enabled() && !Tracer::nvtx()) return issue();
+  const char *name = operation_name(o.scenario);
+  t.range_push(name);
+  const uint64_t t0 = t.now_ns();
+  ACCLRequest *h = issue();
+  const uint64_t cost = t.now_ns() - t0;
+  t.range_pop();
+  if (Tracer::enabled()) t.issue(h, rank, name, o.count, static_cast<unsigned>(o.comm), cost);
+  return h;
+}
+} // namespace
+
 ACCLRequest *ACCL::call_async(CCLO::Options &o) {
   if (!config_rdy && o.scenario != operation::config)
     throw std::runtime_error("ACCL not initialized");
   prepare_call(o);
-  return cclo->start(o);
+  return traced(o, trace_rank_, [&] { return cclo->start(o); });
 }
 
 ACCLRequest *ACCL::call_sync(CCLO::Options &o) {
   if (!config_rdy && o.scenario != operation::config)
     throw std::runtime_error("ACCL not initialized");
   prepare_call(o);
-  return cclo->call(o);
+  ACCLRequest *h = traced(o, trace_rank_, [&] { return cclo->call(o); });
+  if (Tracer::enabled()) Tracer::get().complete(h, cclo->get_retcode(h), cclo->get_duration(h));
+  return h;
+}
+
+void ACCL::free_request(ACCLRequest *request) {
+  if (Tracer::enabled() && request) {
+    try {
+      if (cclo->test(request)) Tracer::get().complete(request, cclo->get_retcode(request), cclo->get_duration(request));
+    } catch (...) { // already freed / unknown: nothing to record
+    }
+  }
+  cclo->free_request(request);
 }
 
 ACCLRequest *ACCL::config_call(cfgFunc fn, unsigned int value, bool run_async, std::vector<ACCLRequest *> &waitfor) {
@@ -370,6 +399,8 @@ void warn_async_sync(const char *fn) {
   do {                                                                       \
     if (run_async) return handle;                                            \
     cclo->wait(handle);                                                      \
+    if (Tracer::enabled())                                                   \
+      Tracer::get().complete(handle, cclo->get_retcode(handle), cclo->get_duration(handle)); \
     post_sync;                                                               \
     check_return_value(fn_name, handle);                                     \
     return handle;                                                           \

@@ -604,3 +604,28 @@ def test_stress_sendrecv_ring(cfg):
                 assert torch.equal(d.host, data(COUNT, prv, salt=i & 7))
         assert torch.equal(d.host, data(COUNT, prv, salt=(iters - 1) & 7))
     A.run_ranks(4, fn, cfg)
+
+
+def test_call_trace_file(tmp_path):
+    """ACCL_TRACE=<prefix>: Chrome trace-event JSON with engine-measured durations."""
+    import json
+    import os
+    import subprocess
+    import sys
+    prefix = str(tmp_path / "trace_")
+    code = ("import accl_b200 as A\n"
+            "def fn(a, r, w):\n"
+            "    s, d = a.create_buffer(256), a.create_buffer(256)\n"
+            "    s.host[:] = r\n"
+            "    a.allreduce(s, d, 256, A.SUM)\n"
+            "    q = a.bcast(s, 256, 0, run_async=True); q.wait(); q.free()\n"
+            "A.run_ranks(2, fn)\n")
+    env = dict(os.environ, ACCL_TRACE=prefix, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env.pop("RANK", None)
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=120)
+    ev = json.load(open(prefix + "0.json"))["traceEvents"]
+    names = [(e["pid"], e["name"]) for e in ev]
+    for r in (0, 1):
+        assert (r, "allreduce") in names and (r, "bcast") in names
+    done = [e for e in ev if e["name"] in ("allreduce", "bcast")]
+    assert all(e["args"]["completed"] and e["args"]["retcode"] == 0 and e["args"]["engine_ns"] > 0 for e in done)
