@@ -106,7 +106,7 @@ def build(with_cuda=True, verbose=False, force=False, tools=True):
             link = [CXX, "-shared", "-fPIC", *[str(o) for o in objs], "-o", str(out), "-lpthread"]
         _run(link, verbose)
     if tools and not with_cuda:
-        for name in ("cclo_emu", "emu_selftest"):
+        for name in ("cclo_emu", "emu_selftest", "emu_suite"):
             build_tool(name, verbose)
     if tools and with_cuda:
         lib_objs = [o for o, s in zip(objs, srcs) if s != BINDING and "bind_" not in s]
@@ -130,7 +130,7 @@ def build_tool(name, verbose=False):
     return exe
 
 
-def build_sanitized(kind="address", verbose=False):
+def build_sanitized(kind="address", verbose=False, tool="emu_selftest"):
     """CPU-only build of the emulator self-test under a sanitizer (`address` = ASan+UBSan,
     `thread` = TSan): build/bin/emu_selftest_<kind>.  The reference configures none
     (SURVEY 5.2); the emulator is the concurrent part of the host code (control thread, data
@@ -138,8 +138,8 @@ def build_sanitized(kind="address", verbose=False):
     BIN.mkdir(parents=True, exist_ok=True)
     flags = {"address": ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"],
              "thread": ["-fsanitize=thread"]}[kind]
-    exe = BIN / f"emu_selftest_{kind}"
-    srcs = [str(CSRC / s) for s in HOST_SOURCES] + [str(CSRC / "tools" / "emu_selftest.cpp")]
+    exe = BIN / f"{tool}_{kind}"
+    srcs = [str(CSRC / s) for s in HOST_SOURCES] + [str(CSRC / "tools" / (tool + ".cpp"))]
     _run([CXX, "-std=c++17", "-O1", "-g", *flags, "-I" + str(CSRC / "include"), *srcs, "-o", str(exe), "-lpthread"],
          verbose)
     return exe
@@ -152,9 +152,10 @@ if __name__ == "__main__":
     ap.add_argument("-v", "--verbose", action="store_true")
     ap.add_argument("-f", "--force", action="store_true")
     ap.add_argument("--no-tools", action="store_true")
-    ap.add_argument("--sanitize", choices=["address", "thread"], help="build build/bin/emu_selftest_<kind> only")
+    ap.add_argument("--sanitize", choices=["address", "thread"], help="build build/bin/<tool>_<kind> only")
+    ap.add_argument("--suite", action="store_true", help="with --sanitize: build the full emu_suite instead of emu_selftest")
     a = ap.parse_args()
     if a.sanitize:
-        print(build_sanitized(a.sanitize, a.verbose))
+        print(build_sanitized(a.sanitize, a.verbose, "emu_suite" if a.suite else "emu_selftest"))
         sys.exit(0)
     print(build(with_cuda=not a.cpu_only, verbose=a.verbose, force=a.force, tools=not a.no_tools))

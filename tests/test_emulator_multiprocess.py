@@ -77,3 +77,14 @@ def test_standalone_engine_processes_with_remote_drivers():
         for p in procs:
             if p.poll() is None:
                 p.kill()
+
+
+def test_cpp_suite_binary():
+    """The C++ API test list (csrc/tools/emu_suite.cpp, counterpart of the reference's gtest binary)."""
+    from accl_b200.utils import build as b
+    exe = os.path.join(ROOT, "build", "bin", "emu_suite")
+    if not os.path.exists(exe):
+        b.build_tool("emu_suite")
+    r = subprocess.run([exe, "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " 0 failed" in r.stdout
