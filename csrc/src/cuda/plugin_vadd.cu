@@ -77,9 +77,7 @@ cudaError_t launch_vadd_allreduce(CudaDevice &dev, uint64_t x_off, uint64_t y_of
   Engine *eng = dev.engine();
   if (!eng) throw std::runtime_error("vadd_allreduce plugin needs the persistent engine (engine=True)");
   ACCL_CUDART(cudaSetDevice(dev.device()));
-  static unsigned int *counter = nullptr; // one per process is enough: plugin launches are stream ordered per device
-  unsigned int *ctr = dev.plugin_counter();
-  (void)counter;
+  unsigned int *ctr = dev.plugin_counter(); // per device: plugin launches are stream ordered
   eng->pin(); // keep the engine resident while a device-side client may issue commands
   const uint32_t grid = static_cast<uint32_t>(std::min<size_t>(148, (count / 4 + 511) / 512 + 1));
   k_plugin_vadd_allreduce<<<grid, 512, 0, stream>>>(dev.world(), x_off, y_off, tmp_off, out_off, count, comm_adr, dpcfg_adr, ctr,

@@ -75,3 +75,73 @@ def test_registered_torch_ops():
         assert torch.all(b == 2.0)
         torch.ops.accl_b200.barrier()
     A.run_ranks(W, fn, CFG)
+
+
+def test_zero_optimizer_matches_plain_sgd():
+    from accl_b200.parallel.strategies import ZeroOptimizer
+    torch.manual_seed(0)
+    w0, b0 = torch.randn(4, 5), torch.randn(7)
+    grads = [[torch.randn(4, 5, generator=torch.Generator().manual_seed(10 * s + r)) for r in range(W)] for s in range(3)]
+
+    def fn(a, r, w):
+        g = TensorGroup(a)
+        pw, pb = w0.clone(), b0.clone()
+        opt = ZeroOptimizer(g, [pw, pb], lr=0.5, momentum=0.9)
+        for s in range(3):
+            opt.grad_views[0].copy_(grads[s][r])
+            opt.grad_views[1].fill_(float(r))
+            opt.step()
+        return pw, pb
+
+    res = A.run_ranks(W, fn, CFG)
+    # reference: plain momentum SGD on the averaged gradients
+    pw, pb, vw, vb = w0.clone(), b0.clone(), torch.zeros(4, 5), torch.zeros(7)
+    for s in range(3):
+        gw, gb = sum(grads[s]) / W, torch.full((7,), sum(range(W)) / W)
+        vw, vb = 0.9 * vw + gw, 0.9 * vb + gb
+        pw, pb = pw - 0.5 * vw, pb - 0.5 * vb
+    for w_, b_ in res:
+        assert torch.allclose(w_, pw, atol=1e-5) and torch.allclose(b_, pb, atol=1e-5)
+
+
+def test_column_parallel_pipeline_moe_ulysses():
+    from accl_b200.parallel.strategies import (ColumnParallelLinear, moe_combine, moe_dispatch, pipeline_recv,
+                                               pipeline_send, ulysses_head_to_seq, ulysses_seq_to_head)
+    S, H, D = 6 * W, 2 * W, 4
+    full = torch.arange(S * H * D, dtype=torch.float32).view(S, H, D)
+
+    def fn(a, r, w):
+        g = TensorGroup(a)
+        # column-parallel linear with gathered output == the unsharded GEMM
+        lin = ColumnParallelLinear(g, 8, 3, gather_output=True)
+        with torch.no_grad():
+            lin.weight.copy_(torch.arange(24, dtype=torch.float32).view(3, 8) + 100 * r)
+        x = torch.ones(5, 8)
+        y = lin(x)
+        ref = torch.cat([x @ (torch.arange(24, dtype=torch.float32).view(3, 8) + 100 * q).t() for q in range(w)], dim=-1)
+        assert torch.equal(y, ref)
+        # pipeline hand-off r -> r + 1 with micro-batch tags
+        act = torch.full((40,), float(r))
+        got = torch.empty(40)
+        reqs = []
+        if r + 1 < w:
+            reqs.append(pipeline_send(g, act, r + 1, microbatch=3))
+        if r > 0:
+            pipeline_recv(g, got, r - 1, microbatch=3)
+            assert torch.all(got == float(r - 1))
+        for q in reqs:
+            q.wait()
+        # MoE dispatch / combine round trip
+        cap, hid = 3, 4
+        routed = torch.stack([torch.full((cap, hid), float(10 * r + q)) for q in range(w)])
+        recv = moe_dispatch(g, routed)
+        for q in range(w):
+            assert torch.all(recv[q] == float(10 * q + r))
+        back = moe_combine(g, recv * 2)
+        assert torch.equal(back, routed * 2)
+        # Ulysses: sequence shard -> head shard -> back
+        mine = full[r * (S // w):(r + 1) * (S // w)].contiguous()
+        heads = ulysses_seq_to_head(g, mine)
+        assert torch.equal(heads, full[:, r * (H // w):(r + 1) * (H // w)])
+        assert torch.equal(ulysses_head_to_seq(g, heads.contiguous()), mine)
+    A.run_ranks(W, fn, CFG)
