@@ -23,9 +23,10 @@ struct GemmRsArgs {
 
 // C = A * W^T computed tile by tile on the 5th-gen tensor cores (TMA ->
 // smem -> tcgen05.mma -> TMEM); every finished accumulator tile is converted
-// to bf16 and added straight into its owner rank's output shard over NVLink
-// (red.global.add.bf16x2 on the peer-mapped heap): reduce-scatter along M with
-// no intermediate buffer and no separate collective.  Returns after enqueueing.
+// to bf16, staged in shared memory and added straight into its owner rank's
+// output shard over NVLink by the TMA unit (cp.reduce.async.bulk.tensor .add on
+// the peer-mapped heap): reduce-scatter along M with no intermediate buffer
+// and no separate collective.  Returns after enqueueing.
 cudaError_t launch_gemm_rs(CudaDevice &dev, const GemmRsArgs &args, cudaStream_t stream);
 
 // vector add whose result feeds an all-reduce issued by the kernel itself

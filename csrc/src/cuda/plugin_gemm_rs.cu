@@ -309,7 +309,7 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> bf16 -> red.add into the owner's shard
+    // ===== epilogue: TMEM -> registers -> bf16 -> swizzled smem -> TMA reduce-add into the owner's shard
     const uint32_t ew = warp - 4; // == warp % 4: this warp owns TMEM lanes [32*ew, 32*ew+32)
     if (lane == 0) {
       uint32_t spins = 0;
