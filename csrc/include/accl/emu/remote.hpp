@@ -63,10 +63,17 @@ public:
   int port() const { return port_; }
 
 private:
-  void send_frame(const wire::Frame &f, const void *payload);
+  // the driver connection; shared with completion hooks that may outlive the server object
+  // (calls still queued in the engine when the driver disconnects)
+  struct Conn {
+    std::mutex m;
+    int fd = -1;
+    void send(const wire::Frame &f, const void *payload);
+    void close();
+  };
   std::shared_ptr<Engine> engine_;
-  int listen_fd_ = -1, fd_ = -1, port_;
-  std::mutex tx_m_;
+  std::shared_ptr<Conn> conn_;
+  int listen_fd_ = -1, port_;
 };
 
 // CCLO backend living in the driver: every operation is a request to the engine process.
@@ -119,6 +126,7 @@ private:
   std::map<uint32_t, Pending> pending_;
   uint32_t next_seq_ = 1;
   std::atomic<bool> stop_{false}, broken_{false};
+  std::shared_ptr<std::atomic<bool>> alive_ = std::make_shared<std::atomic<bool>>(true);
   std::thread reader_;
   RequestRegistry requests_;
   std::mutex calls_m_;

@@ -49,7 +49,7 @@ sockaddr_in make_addr(const std::string &addr, int port) {
 
 // ------------------------------------------------------------------ server
 EngineServer::EngineServer(std::shared_ptr<Engine> engine, const std::string &addr, int port)
-    : engine_(std::move(engine)), port_(port) {
+    : engine_(std::move(engine)), conn_(std::make_shared<Conn>()), port_(port) {
   listen_fd_ = ::socket(AF_INET, SOCK_STREAM, 0);
   int one = 1;
   setsockopt(listen_fd_, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
@@ -60,27 +60,37 @@ EngineServer::EngineServer(std::shared_ptr<Engine> engine, const std::string &ad
 }
 
 EngineServer::~EngineServer() {
-  if (fd_ >= 0) ::close(fd_);
+  conn_->close();
   if (listen_fd_ >= 0) ::close(listen_fd_);
 }
 
-void EngineServer::send_frame(const Frame &f, const void *payload) {
-  std::lock_guard<std::mutex> g(tx_m_);
-  if (fd_ < 0) return;
-  if (!tx_all(fd_, &f, sizeof(f)) || (f.len && !tx_all(fd_, payload, f.len))) ACCL_DEBUG_LOG("EngineServer: driver went away");
+void EngineServer::Conn::send(const Frame &f, const void *payload) {
+  std::lock_guard<std::mutex> g(m);
+  if (fd < 0) return;
+  if (!tx_all(fd, &f, sizeof(f)) || (f.len && !tx_all(fd, payload, f.len))) ACCL_DEBUG_LOG("EngineServer: driver went away");
+}
+
+void EngineServer::Conn::close() {
+  std::lock_guard<std::mutex> g(m);
+  if (fd >= 0) ::close(fd);
+  fd = -1;
 }
 
 void EngineServer::serve() {
-  fd_ = ::accept(listen_fd_, nullptr, nullptr);
-  if (fd_ < 0) throw std::runtime_error("EngineServer: accept failed");
+  const int fd = ::accept(listen_fd_, nullptr, nullptr);
+  if (fd < 0) throw std::runtime_error("EngineServer: accept failed");
   int on = 1;
-  setsockopt(fd_, IPPROTO_TCP, TCP_NODELAY, &on, sizeof(on));
+  setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &on, sizeof(on));
+  {
+    std::lock_guard<std::mutex> g(conn_->m);
+    conn_->fd = fd;
+  }
   std::vector<uint8_t> payload;
   for (;;) {
     Frame f;
-    if (!rx_all(fd_, &f, sizeof(f))) break; // driver disconnected
+    if (!rx_all(fd, &f, sizeof(f))) break; // driver disconnected
     payload.resize(f.len);
-    if (f.len && !rx_all(fd_, payload.data(), f.len)) break;
+    if (f.len && !rx_all(fd, payload.data(), f.len)) break;
     Frame r;
     r.type = wire::REPLY;
     r.seq = f.seq;
@@ -105,14 +115,14 @@ void EngineServer::serve() {
         c.req = req;
         const uint64_t id = f.a;
         // runs on the engine's control thread after the request has been completed
-        c.on_done = [this, id, req](uint32_t rc) {
+        c.on_done = [conn = conn_, id, req](uint32_t rc) {
           Frame e;
           e.type = wire::EVENT_DONE;
           e.a = id;
           e.b = rc;
           const uint64_t dur = req->duration_ns();
           e.len = sizeof(dur);
-          send_frame(e, &dur);
+          conn->send(e, &dur);
         };
         engine_->submit(std::move(c));
         break;
@@ -138,19 +148,18 @@ void EngineServer::serve() {
       out.assign(s.begin(), s.end());
     }
     r.len = static_cast<uint32_t>(out.size());
-    send_frame(r, out.data());
+    conn_->send(r, out.data());
     if (quit) break;
   }
-  std::lock_guard<std::mutex> g(tx_m_);
-  ::close(fd_);
-  fd_ = -1;
+  conn_->close();
 }
 
 // ------------------------------------------------------------------ client
 namespace {
 class RemoteStorage : public BufferStorage {
 public:
-  RemoteStorage(RemoteDevice *d, size_t bytes, bufferKind kind, void *wrap) : dev_(d), bytes_(bytes), kind_(kind) {
+  RemoteStorage(RemoteDevice *d, std::shared_ptr<std::atomic<bool>> alive, size_t bytes, bufferKind kind, void *wrap)
+      : dev_(d), alive_(std::move(alive)), bytes_(bytes), kind_(kind) {
     addr_ = dev_->mem_alloc(std::max<size_t>(bytes, 1), kind == bufferKind::host_only);
     if (wrap) host_ = static_cast<uint8_t *>(wrap);
     else {
@@ -160,7 +169,7 @@ public:
   }
   ~RemoteStorage() override {
     try {
-      dev_->mem_free(addr_);
+      if (alive_->load()) dev_->mem_free(addr_); // a buffer may outlive its device (interpreter shutdown order)
     } catch (...) {
     }
   }
@@ -178,6 +187,7 @@ public:
 
 private:
   RemoteDevice *dev_;
+  std::shared_ptr<std::atomic<bool>> alive_;
   size_t bytes_;
   bufferKind kind_;
   uint64_t addr_ = 0;
@@ -205,6 +215,7 @@ RemoteDevice::RemoteDevice(const std::string &addr, int port, int global_rank, i
 }
 
 RemoteDevice::~RemoteDevice() {
+  alive_->store(false);
   stop_ = true;
   if (fd_ >= 0) ::shutdown(fd_, SHUT_RDWR);
   if (reader_.joinable()) reader_.join();
@@ -429,10 +440,10 @@ std::string RemoteDevice::describe() {
 void RemoteDevice::printDebug() { ACCL_INFO_LOG(debug_state()); }
 
 std::shared_ptr<BufferStorage> RemoteDevice::allocate(size_t bytes, bufferKind kind) {
-  return std::make_shared<RemoteStorage>(this, bytes, kind, nullptr);
+  return std::make_shared<RemoteStorage>(this, alive_, bytes, kind, nullptr);
 }
 std::shared_ptr<BufferStorage> RemoteDevice::wrap_host(void *host_ptr, size_t bytes) {
-  return std::make_shared<RemoteStorage>(this, bytes, bufferKind::device, host_ptr);
+  return std::make_shared<RemoteStorage>(this, alive_, bytes, bufferKind::device, host_ptr);
 }
 
 } // namespace emu
