@@ -106,7 +106,7 @@ def build(with_cuda=True, verbose=False, force=False, tools=True):
             link = [CXX, "-shared", "-fPIC", *[str(o) for o in objs], "-o", str(out), "-lpthread"]
         _run(link, verbose)
     if tools and not with_cuda:
-        for name in ("cclo_emu", "emu_selftest", "emu_suite"):
+        for name in ("cclo_emu", "emu_selftest", "emu_suite", "emu_bench"):
             build_tool(name, verbose)
     if tools and with_cuda:
         lib_objs = [o for o, s in zip(objs, srcs) if s != BINDING and "bind_" not in s]

@@ -629,3 +629,72 @@ def test_call_trace_file(tmp_path):
         assert (r, "allreduce") in names and (r, "bcast") in names
     done = [e for e in ev if e["name"] in ("allreduce", "bcast")]
     assert all(e["args"]["completed"] and e["args"]["retcode"] == 0 and e["args"]["engine_ns"] > 0 for e in done)
+
+
+# ------------------------------------------------------------ device-side API through the BFM hooks
+# (reference test/host/hls_simulator/test.cpp:54-250, run against an emulator without kernel loopback)
+OP_SEND, OP_RECV, OP_REDUCE = 3, 4, 8
+OP0_STREAM, RES_STREAM = 1, 2
+
+
+def _desc(a, scenario, count, root_src_dst=0, function=0, tag=A.TAG_ANY, stream_flags=0, addr0=0, addr2=0):
+    """The 15-word descriptor a kernel emits with accl::device::Command::start_call."""
+    return [scenario, count, 0, root_src_dst, function, tag, a.get_arithmetic_config_addr(DataType.float32, DataType.float32),
+            0, stream_flags, addr0 & 0xFFFFFFFF, addr0 >> 32, 0, 0, addr2 & 0xFFFFFFFF, addr2 >> 32]
+
+
+def _f32(t):
+    return t.numpy().astype(np.float32).tobytes()
+
+
+def test_bfm_vadd_put():
+    """A 'user kernel' adds 1 to its input and stream_puts the result into the next rank's stream 9, issuing
+    the command itself (reference vadd_put.cpp:25-86, hls_simulator/test.cpp:54)."""
+    n = 64
+
+    def fn(a, r, w):
+        a.emu_set_kernel_loopback(False)
+        x = data(n, r)
+        a.barrier()
+        # kernel body: compute, push the data words, then the command (send, operand from stream, result to stream 9)
+        a.emu_kernel_push(_f32(x + 1))
+        assert a.emu_device_call(_desc(a, OP_SEND, n, root_src_dst=(r + 1) % w, tag=9, stream_flags=OP0_STREAM | RES_STREAM)) == 0
+        got = np.frombuffer(a.emu_kernel_pull(9, n * 4), dtype=np.float32)
+        assert np.array_equal(got, (data(n, (r - 1) % w) + 1).numpy())
+    A.run_ranks(2, fn, EAGER)
+
+
+def test_bfm_loopback_through_user_kernel():
+    """send -> recv-to-stream -> user kernel loop -> send-from-stream -> recv (hls_simulator/test.cpp:153)."""
+    n = 128
+
+    def fn(a, r, w):
+        a.emu_set_kernel_loopback(False)
+        s, d = a.create_buffer(n), a.create_buffer(n)
+        s.host[:] = data(n, r)
+        nxt, prv = (r + 1) % w, (r - 1) % w
+        req = a.send(s, n, nxt, tag=5, run_async=True)
+        a.recv_to_stream(DataType.float32, n, prv, tag=5)          # network -> stream <tag> (the kernel's input)
+        req.wait()
+        words = a.emu_kernel_pull(5, n * 4)                        # the user kernel: read, transform, write back
+        a.emu_kernel_push((np.frombuffer(words, dtype=np.float32) * 2).tobytes())
+        req = a.send_from_stream(DataType.float32, n, nxt, tag=6, run_async=True)
+        a.recv(d, n, prv, tag=6)
+        req.wait()
+        assert torch.equal(d.host, data(n, (r - 2) % w) * 2)
+    A.run_ranks(3, fn, EAGER)
+
+
+def test_bfm_reduce_stream_to_stream():
+    """Every rank's kernel feeds the reduction from its output stream; the root's kernel receives the result
+    on its input stream (hls_simulator/test.cpp:199 `test_reduce_stream`)."""
+    n = 96
+
+    def fn(a, r, w):
+        a.emu_set_kernel_loopback(False)
+        a.emu_kernel_push(_f32(data(n, r)))
+        a.reduce_stream2stream(DataType.float32, DataType.float32, n, 1, SUM)
+        if r == 1:
+            got = torch.from_numpy(np.frombuffer(a.emu_kernel_pull(0, n * 4), dtype=np.float32).copy())
+            assert close(got, reduce_ref(w, n, SUM), 1e-5, 1e-5)
+    A.run_ranks(3, fn, EAGER)
