@@ -136,5 +136,5 @@ def test_user_kernel_in_the_stream_path():
         # data made two hops: it comes from the rank two places behind me, plus one
         src = (r - 2) % w
         assert torch.equal(d.host, torch.arange(n, dtype=torch.float32) + 100 * src + 1)
-    A.run_cuda_ranks(devices(2), fn, dict(n_egr_rx_bufs=4, egr_rx_buf_size=16 << 10, max_egr_size=16 << 10,
+    A.run_cuda_ranks([0, 0], fn, dict(n_egr_rx_bufs=4, egr_rx_buf_size=16 << 10, max_egr_size=16 << 10,
                                           max_rndzv_size=1 << 26), heap_mb=64, max_ctas=4)
