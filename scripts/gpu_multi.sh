@@ -29,3 +29,5 @@ for l in sys.stdin:
 "
 echo "--- gemm -> reduce_scatter"
 timeout 300 $TR --master-port 29559 bench/gemm_rs.py --gm 8192 --gn 8192 --gk 2048 --check --out gpurun_out/gemm_rs_${N}gpu.jsonl 2>/dev/null | tail -1 | cut -c1-600
+echo "--- vector-add plugin -> all-reduce (device-issued)"
+timeout 300 $TR --master-port 29561 bench/vadd.py --min-log2 12 --max-log2 26 --step 2 --out gpurun_out/vadd_${N}gpu.jsonl 2>/dev/null | cut -c1-200
