@@ -6,6 +6,7 @@
 #include "accl/accl.hpp"
 #include "accl/cuda/cudadevice.hpp"
 #include "accl/cuda/driver_api.hpp"
+#include "accl/cuda/plan.hpp"
 #include "accl/cuda/plugins.hpp"
 
 namespace py = pybind11;
@@ -29,6 +30,35 @@ static CudaConfig make_cfg(int device, size_t heap_mb, bool multicast, int max_c
 
 void bind_cuda(py::module_ &m) {
   m.def("cuda_driver_available", [] { return DriverApi::available(); });
+  // The call planner (plan.hpp) as a pure function, for unit tests on machines without a GPU: which protocol /
+  // algorithm / channel count a call of `count` elements of `dtype` gets on a communicator of `world` ranks.
+  m.def("cuda_plan", [](operation op, uint32_t count, dataType dtype, uint32_t world, uint32_t max_eager_bytes, uint32_t max_ctas,
+                        bool has_mc, uint32_t nvls_min_ranks, uint64_t oneshot_max_bytes, bool compressed) {
+    std::vector<uint32_t> exch(exchmem::SIZE_WORDS, 0);
+    exch[exchmem::MAX_EAGER_SIZE / 4] = max_eager_bytes;
+    PlanCfg cfg{};
+    cfg.max_ctas = max_ctas;
+    cfg.nvls_min_ranks = nvls_min_ranks;
+    cfg.has_mc = has_mc ? 1 : 0;
+    cfg.heap_world = world;
+    cfg.oneshot_max_bytes = oneshot_max_bytes;
+    cfg.nvls_ops = NVLS_OPS_DEFAULT;
+    WorkItem w{};
+    w.desc.scenario = static_cast<uint32_t>(op);
+    w.desc.count = count;
+    w.desc.compression_flags = compressed ? 1u : 0u;
+    w.comm_size = world;
+    w.udtype = static_cast<uint32_t>(dtype);
+    plan_call(exch.data(), cfg, w);
+    static const char *names[] = {"auto", "local", "eager", "nvls", "p2p", "p2p_oneshot"};
+    py::dict d;
+    d["algo"] = w.algo < 6 ? names[w.algo] : "?";
+    d["n_ctas"] = w.n_ctas;
+    d["use_mc"] = (w.flags & WF_USE_MC) != 0;
+    return d;
+  }, py::arg("op"), py::arg("count"), py::arg("dtype"), py::arg("world"), py::arg("max_eager_bytes") = 65536,
+        py::arg("max_ctas") = 128, py::arg("has_mc") = true, py::arg("nvls_min_ranks") = 3,
+        py::arg("oneshot_max_bytes") = 2u << 20, py::arg("compressed") = false);
   m.def("cuda_debug_state", [](ACCL &a) {
     auto *d = dynamic_cast<CudaDevice *>(a.device());
     if (!d) throw std::runtime_error("not a CUDA backend");
