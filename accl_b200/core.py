@@ -117,9 +117,14 @@ class Accl:
 
     # ---- setup -----------------------------------------------------------
     @staticmethod
-    def generate_ranks(world, base_port=5500, max_segment_size=1024, ips=None):
-        """Synthetic rank table (reference: accl_network_utils::generate_ranks)."""
-        return [_C.Rank(ips[i] if ips else "127.0.0.1", base_port + i, i, max_segment_size) for i in range(world)]
+    def generate_ranks(world=None, base_port=5500, max_segment_size=1024, ips=None, config_file=None):
+        """Rank table (reference: accl_network_utils::generate_ranks): from a list of IPs, from the reference's
+        JSON rank file {"ips": [...]} (`config_file`), or `world` local ranks on 127.0.0.1."""
+        if config_file is not None:
+            return _C.generate_ranks_from_file(str(config_file), base_port, max_segment_size)
+        if ips is None:
+            ips = ["127.0.0.1"] * world
+        return _C.generate_ranks(list(ips), base_port, max_segment_size)
 
     def initialize(self, ranks=None, local_rank=None, n_egr_rx_bufs=16, egr_rx_buf_size=1024, max_egr_size=1024,
                    max_rndzv_size=32 * 1024):

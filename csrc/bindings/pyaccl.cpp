@@ -338,6 +338,15 @@ PYBIND11_MODULE(_C, m) {
     return rd->debug_state();
   }, gil_release());
 
+  // ---- rank tables
+  m.def("generate_ranks", [](const std::vector<std::string> &ips, int base_port, addr_t rxbuf_size) {
+    return generate_ranks(ips, base_port, rxbuf_size);
+  }, py::arg("ips"), py::arg("base_port") = 5500, py::arg("rxbuf_size") = 1024);
+  m.def("generate_ranks_from_file", [](const std::string &path, int base_port, addr_t rxbuf_size) {
+    return generate_ranks(path, base_port, rxbuf_size);
+  }, py::arg("config_file"), py::arg("base_port") = 5500, py::arg("rxbuf_size") = 1024);
+  m.def("get_ips", [](const std::string &path) { return get_ips(path); });
+
   // ---- numerics helpers used by tests as the reference for narrow floats
   m.def("encode_float", [](float f, dataType t) -> uint32_t {
     switch (t) {

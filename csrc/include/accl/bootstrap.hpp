@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+#include "accl/communicator.hpp"
+
 namespace accl {
 
 class Oob {
@@ -100,5 +102,15 @@ private:
 // and the NVLS multicast object.  all_to_all_fds(): every rank contributes
 // one fd and receives everybody's (its own slot is a dup of its own fd).
 std::vector<int> exchange_fds(Oob &oob, int my_fd, const std::string &channel);
+
+// ---- rank tables (reference accl_network_utils::generate_ranks / get_ips, accl_network_utils.cpp:394-449)
+// IPs from a JSON configuration file of the form {"ips": ["10.0.0.1", "10.0.0.2", ...]} (the reference's -c file).
+std::vector<std::string> get_ips(const std::string &config_file);
+// local: everybody on 127.0.0.1; otherwise the reference's 10.10.10.<rank + 1> convention
+std::vector<std::string> get_ips(bool local, int world_size);
+// rank i = {ips[i], base_port + i, session id i, max eager segment rxbuf_size}
+std::vector<rank_t> generate_ranks(const std::vector<std::string> &ips, int base_port, addr_t rxbuf_size);
+std::vector<rank_t> generate_ranks(bool local, int world_size, int base_port, addr_t rxbuf_size);
+std::vector<rank_t> generate_ranks(const std::string &config_file, int base_port, addr_t rxbuf_size);
 
 } // namespace accl

@@ -12,6 +12,8 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
+#include <sstream>
 #include <mutex>
 #include <random>
 #include <stdexcept>
@@ -268,6 +270,52 @@ std::vector<int> exchange_fds(Oob &oob, int my_fd, const std::string &channel) {
   oob.barrier();
   ::close(lfd);
   return out;
+}
+
+// ------------------------------------------------------------ rank tables
+std::vector<std::string> get_ips(const std::string &config_file) {
+  std::ifstream f(config_file);
+  if (!f.good()) throw std::runtime_error("cannot open rank configuration file " + config_file);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  const std::string txt = ss.str();
+  // minimal JSON: find the "ips" key and take every quoted string up to the closing bracket
+  size_t k = txt.find("\"ips\"");
+  if (k == std::string::npos) throw std::runtime_error("IPs not specified in config file");
+  size_t open = txt.find('[', k), close = txt.find(']', k);
+  if (open == std::string::npos || close == std::string::npos || close < open)
+    throw std::runtime_error("malformed \"ips\" array in " + config_file);
+  std::vector<std::string> ips;
+  size_t p = open;
+  while (true) {
+    size_t a = txt.find('"', p + 1);
+    if (a == std::string::npos || a > close) break;
+    size_t b = txt.find('"', a + 1);
+    if (b == std::string::npos || b > close) throw std::runtime_error("malformed \"ips\" array in " + config_file);
+    ips.push_back(txt.substr(a + 1, b - a - 1));
+    p = b;
+  }
+  if (ips.empty()) throw std::runtime_error("IPs not specified in config file");
+  return ips;
+}
+
+std::vector<std::string> get_ips(bool local, int world_size) {
+  std::vector<std::string> ips;
+  for (int i = 0; i < world_size; ++i) ips.push_back(local ? "127.0.0.1" : "10.10.10." + std::to_string(i + 1));
+  return ips;
+}
+
+std::vector<rank_t> generate_ranks(const std::vector<std::string> &ips, int base_port, addr_t rxbuf_size) {
+  std::vector<rank_t> ranks;
+  for (size_t i = 0; i < ips.size(); ++i)
+    ranks.emplace_back(ips[i], base_port + static_cast<int>(i), static_cast<int>(i), rxbuf_size);
+  return ranks;
+}
+std::vector<rank_t> generate_ranks(bool local, int world_size, int base_port, addr_t rxbuf_size) {
+  return generate_ranks(get_ips(local, world_size), base_port, rxbuf_size);
+}
+std::vector<rank_t> generate_ranks(const std::string &config_file, int base_port, addr_t rxbuf_size) {
+  return generate_ranks(get_ips(config_file), base_port, rxbuf_size);
 }
 
 } // namespace accl

@@ -698,3 +698,39 @@ def test_bfm_reduce_stream_to_stream():
             got = torch.from_numpy(np.frombuffer(a.emu_kernel_pull(0, n * 4), dtype=np.float32).copy())
             assert close(got, reduce_ref(w, n, SUM), 1e-5, 1e-5)
     A.run_ranks(3, fn, EAGER)
+
+
+def test_rank_table_helpers(tmp_path):
+    """generate_ranks / get_ips (reference accl_network_utils.cpp:394-449): IP list, JSON rank file, local default."""
+    cfg = tmp_path / "ranks.json"
+    cfg.write_text('{"ips": ["10.1.0.1", "10.1.0.2",\\n "10.1.0.3"], "other": [1, 2]}')
+    assert A._C.get_ips(str(cfg)) == ["10.1.0.1", "10.1.0.2", "10.1.0.3"]
+    ranks = A.Accl.generate_ranks(config_file=cfg, base_port=6000, max_segment_size=2048)
+    assert [(r.ip, r.port, r.session_id, r.max_segment_size) for r in ranks] == [
+        ("10.1.0.1", 6000, 0, 2048), ("10.1.0.2", 6001, 1, 2048), ("10.1.0.3", 6002, 2, 2048)]
+    local = A.Accl.generate_ranks(4)
+    assert [r.ip for r in local] == ["127.0.0.1"] * 4 and [r.port for r in local] == [5500, 5501, 5502, 5503]
+    (tmp_path / "bad.json").write_text('{"nodes": []}')
+    with pytest.raises(RuntimeError):
+        A._C.get_ips(str(tmp_path / "bad.json"))
+
+    # an explicit table drives initialize() like the synthetic one
+    def fn(a, r, w):
+        s, d = a.create_buffer(32), a.create_buffer(32)
+        s.host[:] = r + 1
+        a.allreduce(s, d, 32, SUM)
+        assert torch.all(d.host == 3)
+    accls = A.emulator_world(2)
+    import threading
+    errs = []
+
+    def body(r):
+        try:
+            accls[r].initialize(A.Accl.generate_ranks(ips=["127.0.0.1", "127.0.0.1"]), r)
+            fn(accls[r], r, 2)
+        except BaseException as e:  # noqa: BLE001
+            errs.append(repr(e))
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(2)]
+    [t.start() for t in ts]
+    [t.join(60) for t in ts]
+    assert not errs, errs
