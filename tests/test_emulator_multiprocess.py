@@ -88,3 +88,16 @@ def test_cpp_suite_binary():
     r = subprocess.run([exe, "3"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " 0 failed" in r.stdout
+
+
+@pytest.mark.parametrize("zero", [0, 1])
+def test_data_parallel_mlp_trains(zero):
+    """End-to-end consumer: DDP / ZeRO-1 training of a small MLP, one emulator process per rank."""
+    import json
+    r = subprocess.run([sys.executable, "-m", "accl_b200.models.emulator", "-n", "2", "--", sys.executable, "-m",
+                        "accl_b200.models.dp_mlp", "--zero", str(zero), "--steps", "20"], cwd=ROOT, capture_output=True,
+                       text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][0]
+    out = json.loads(line)
+    assert out["ok"] and out["replicas_identical"] and out["loss_last"] < out["loss_first"]
