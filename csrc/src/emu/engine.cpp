@@ -303,6 +303,7 @@ void Engine::ingress_loop() {
         std::lock_guard<std::mutex> g(rx_m_);
         rx_overflow_.push_back(std::move(p));
         rx_try_fill_locked();
+        if (!rx_overflow_.empty()) rx_cv_.notify_all(); // pool exhausted: a seeker may want to swap this one in
       }
       break;
     case MsgType::RNDZVS_MSG: {
@@ -350,7 +351,64 @@ int Engine::rx_seek(uint32_t comm_sig, uint32_t src_global, uint32_t tag, uint32
     }
     return false;
   };
-  rx_cv_.wait_for(lk, std::chrono::microseconds(tmo_us), [&] { return stop_.load() || scan(); });
+  // The pool fills in arrival order.  When it is exhausted by messages nobody is asking for yet (many
+  // peers, few buffers: all-to-all, gather fan-in) the one being sought may sit in the overflow queue
+  // forever.  Swap it in: a parked message goes back to the queue, the sought one takes its buffer.
+  auto swap_in = [&]() -> bool {
+    for (auto it = rx_overflow_.begin(); it != rx_overflow_.end(); ++it) {
+      const Packet &p = *it;
+      if (p.hdr.src != src_global || p.hdr.seqn != seqn || p.hdr.comm_sig != comm_sig) continue;
+      if (tag != TAG_ANY && p.hdr.tag != tag) continue;
+      std::lock_guard<std::mutex> e(exch_m_);
+      const uint32_t n = exch_[exchmem::EAGER_RX_BUF_COUNT / 4];
+      for (uint32_t i = 0; i < n; ++i) {
+        if (exch_[exchmem::rxbuf_offset(i, exchmem::RX_STATUS) / 4] != exchmem::RX_RESERVED) continue;
+        const uint32_t maxlen = exch_[exchmem::rxbuf_offset(i, exchmem::RX_MAX_LEN) / 4];
+        if (p.payload.size() > maxlen) continue;
+        const uint64_t addr = (static_cast<uint64_t>(exch_[exchmem::rxbuf_offset(i, exchmem::RX_ADDR_HI) / 4]) << 32) |
+                              exch_[exchmem::rxbuf_offset(i, exchmem::RX_ADDR_LO) / 4];
+        uint32_t err = 0;
+        uint8_t *buf = mem_ptr(addr, maxlen, err);
+        if (!buf) continue;
+        // evict buffer i into a packet ...
+        Packet parked;
+        parked.hdr.src = exch_[exchmem::rxbuf_offset(i, exchmem::RX_SRC) / 4];
+        parked.hdr.dst = static_cast<uint32_t>(rank_);
+        parked.hdr.seqn = exch_[exchmem::rxbuf_offset(i, exchmem::RX_SEQ) / 4];
+        parked.hdr.tag = exch_[exchmem::rxbuf_offset(i, exchmem::RX_TAG) / 4];
+        const uint32_t len = exch_[exchmem::rxbuf_offset(i, exchmem::RX_LEN) / 4];
+        if (i < rx_meta_.size()) {
+          parked.hdr.comm_sig = rx_meta_[i].comm_sig;
+          parked.hdr.elems = rx_meta_[i].elems;
+          parked.hdr.dtypes = rx_meta_[i].dtypes;
+        }
+        parked.payload.assign(buf, buf + len);
+        // ... and land the sought message in its place
+        if (!p.payload.empty()) std::memcpy(buf, p.payload.data(), p.payload.size());
+        if (rx_meta_.size() <= i) rx_meta_.resize(i + 1);
+        rx_meta_[i] = RxMeta{p.hdr.comm_sig, p.hdr.elems, p.hdr.dtypes};
+        exch_[exchmem::rxbuf_offset(i, exchmem::RX_TAG) / 4] = p.hdr.tag;
+        exch_[exchmem::rxbuf_offset(i, exchmem::RX_LEN) / 4] = static_cast<uint32_t>(p.payload.size());
+        exch_[exchmem::rxbuf_offset(i, exchmem::RX_SRC) / 4] = p.hdr.src;
+        exch_[exchmem::rxbuf_offset(i, exchmem::RX_SEQ) / 4] = p.hdr.seqn;
+        rx_overflow_.erase(it);
+        rx_overflow_.push_back(std::move(parked));
+        found = static_cast<int>(i);
+        return true;
+      }
+      return false; // sought message is here but no buffer can take it
+    }
+    return false;
+  };
+  const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(tmo_us);
+  while (!stop_.load()) {
+    if (scan()) break;
+    if (!rx_overflow_.empty() && swap_in()) break;
+    if (rx_cv_.wait_until(lk, deadline) == std::cv_status::timeout) {
+      if (!scan() && !rx_overflow_.empty()) swap_in();
+      break;
+    }
+  }
   return found;
 }
 

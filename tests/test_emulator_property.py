@@ -1,0 +1,112 @@
+"""Property tests (hypothesis) on the CPU emulator: random counts, world sizes, roots, reduce functions and —
+most importantly — random eager / rendezvous geometry (rx buffer size, eager threshold, rendezvous segment size),
+so that segmentation boundaries, protocol switch-over points and non-divisible counts are hit from every side.
+Results are compared with a plain torch reference.  The reference's suite probes only k * segment +- 1
+(test/host/xrt/src/test.cpp:345-393)."""
+import torch
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import accl_b200 as A
+from accl_b200 import MAX, SUM
+
+OPS = ["sendrecv", "bcast", "scatter", "gather", "allgather", "reduce", "allreduce", "reduce_scatter", "alltoall"]
+
+
+def data(n, r, salt):
+    g = torch.Generator().manual_seed(977 * salt + 31 * r + 5)
+    return torch.randint(-64, 64, (n,), generator=g).float()  # exactly representable: sums compare with ==
+
+
+@st.composite
+def geometry(draw):
+    buf = draw(st.sampled_from([64, 128, 256, 1024, 4096]))
+    max_egr = draw(st.sampled_from([64, 256, 1024, 4096, 1 << 20]))
+    # the engine needs an eager message to fit the rx pool: keep threshold <= pool capacity
+    n_bufs = draw(st.sampled_from([8, 16, 32]))
+    max_egr = min(max_egr, buf * n_bufs // 2) if max_egr < (1 << 20) else max_egr
+    max_egr = max(max_egr, buf)      # the engine rejects an eager threshold below one rx buffer
+    rndzv = draw(st.sampled_from([256, 1024, 32 * 1024, 1 << 20]))
+    rndzv = max(rndzv, 2 * max_egr)  # the engine rejects a rendezvous segment size below the eager threshold
+    return dict(n_egr_rx_bufs=n_bufs, egr_rx_buf_size=buf, max_egr_size=max_egr, max_rndzv_size=rndzv)
+
+
+def run_op(a, r, w, op, count, root, func, salt):
+    def red(vs):
+        out = vs[0].clone()
+        for v in vs[1:]:
+            out = out + v if func == SUM else torch.maximum(out, v)
+        return out
+
+    if op == "sendrecv":
+        s, d = a.create_buffer(count), a.create_buffer(count)
+        s.host[:] = data(count, r, salt)
+        nxt, prv = (r + 1) % w, (r - 1) % w
+        req = a.send(s, count, nxt, tag=salt & 0xFF, run_async=True)
+        a.recv(d, count, prv, tag=salt & 0xFF)
+        req.wait()
+        assert torch.equal(d.host, data(count, prv, salt))
+    elif op == "bcast":
+        b = a.create_buffer(count)
+        b.host[:] = data(count, r, salt)
+        a.bcast(b, count, root)
+        assert torch.equal(b.host, data(count, root, salt))
+    elif op == "scatter":
+        s, d = a.create_buffer(count * w), a.create_buffer(count)
+        s.host[:] = data(count * w, r, salt)
+        a.scatter(s, d, count, root)
+        assert torch.equal(d.host, data(count * w, root, salt)[r * count:(r + 1) * count])
+    elif op == "gather":
+        s, d = a.create_buffer(count), a.create_buffer(count * w)
+        s.host[:] = data(count, r, salt)
+        a.gather(s, d, count, root)
+        if r == root:
+            assert torch.equal(d.host, torch.cat([data(count, q, salt) for q in range(w)]))
+    elif op == "allgather":
+        s, d = a.create_buffer(count), a.create_buffer(count * w)
+        s.host[:] = data(count, r, salt)
+        a.allgather(s, d, count)
+        assert torch.equal(d.host, torch.cat([data(count, q, salt) for q in range(w)]))
+    elif op == "reduce":
+        s, d = a.create_buffer(count), a.create_buffer(count)
+        s.host[:] = data(count, r, salt)
+        a.reduce(s, d, count, root, func)
+        if r == root:
+            assert torch.equal(d.host, red([data(count, q, salt) for q in range(w)]))
+    elif op == "allreduce":
+        s, d = a.create_buffer(count), a.create_buffer(count)
+        s.host[:] = data(count, r, salt)
+        a.allreduce(s, d, count, func)
+        assert torch.equal(d.host, red([data(count, q, salt) for q in range(w)]))
+    elif op == "reduce_scatter":
+        s, d = a.create_buffer(count * w), a.create_buffer(count)
+        s.host[:] = data(count * w, r, salt)
+        a.reduce_scatter(s, d, count, func)
+        assert torch.equal(d.host, red([data(count * w, q, salt) for q in range(w)])[r * count:(r + 1) * count])
+    elif op == "alltoall":
+        s, d = a.create_buffer(count * w), a.create_buffer(count * w)
+        s.host[:] = data(count * w, r, salt)
+        a.alltoall(s, d, count)
+        exp = torch.cat([data(count * w, q, salt)[r * count:(r + 1) * count] for q in range(w)])
+        assert torch.equal(d.host, exp)
+    else:
+        a.barrier()
+
+
+step = st.tuples(st.sampled_from(OPS + ["barrier"]), st.integers(1, 3000), st.integers(0, 5), st.sampled_from([SUM, MAX]),
+                 st.integers(0, 1000))
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(world=st.integers(2, 6), steps=st.lists(step, min_size=1, max_size=5), cfg=geometry())
+def test_collectives_match_reference(world, steps, cfg):
+    """A random program of 1-5 calls on one world: sequence numbers, rx-pool reuse and parked calls carry over
+    from one call to the next."""
+    always_eager = cfg["max_egr_size"] >= (1 << 20)
+    if always_eager:
+        # messages must fit the rx pool as a whole
+        cfg = dict(cfg, egr_rx_buf_size=4096, n_egr_rx_bufs=32)
+
+    def fn(a, r, w):
+        for op, count, root, func, salt in steps:
+            run_op(a, r, w, op, min(count, 2000) if always_eager else count, root % w, func, salt)
+    A.run_ranks(world, fn, cfg, timeout=120.0)
