@@ -110,3 +110,73 @@ def test_collectives_match_reference(world, steps, cfg):
         for op, count, root, func, salt in steps:
             run_op(a, r, w, op, min(count, 2000) if always_eager else count, root % w, func, salt)
     A.run_ranks(world, fn, cfg, timeout=120.0)
+
+
+DTYPES = [torch.float32, torch.float16, torch.bfloat16, torch.float64, torch.int32, torch.int64]
+
+
+@settings(max_examples=100, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(op=st.sampled_from(["sendrecv", "bcast", "allgather", "reduce", "allreduce", "reduce_scatter"]),
+       world=st.integers(2, 4), count=st.integers(1, 1500), root=st.integers(0, 3), func=st.sampled_from([SUM, MAX]),
+       dtype=st.sampled_from(DTYPES), wire=st.sampled_from([None, torch.float16, torch.bfloat16]), cfg=geometry(),
+       salt=st.integers(0, 100))
+def test_dtypes_and_wire_compression(op, world, count, root, func, dtype, wire, cfg, salt):
+    """Every element type, and fp32 over a narrower wire type.  Values are small integers, so every sum is
+    exactly representable in every format involved and results must match bit for bit."""
+    root %= world
+    if dtype != torch.float32:
+        wire = None  # compression pairs are registered for fp32 operands
+    if cfg["max_egr_size"] >= (1 << 20) or wire is not None:
+        # compressed calls are always eager: size the pool for whole messages
+        cfg = dict(cfg, egr_rx_buf_size=4096, n_egr_rx_bufs=32, max_egr_size=max(cfg["max_egr_size"], 4096),
+                   max_rndzv_size=max(cfg["max_rndzv_size"], 1 << 24))
+        count = min(count, 1000)
+
+    def vals(n, r):
+        g = torch.Generator().manual_seed(131 * salt + 7 * r + 3)
+        return torch.randint(-16, 16, (n,), generator=g).to(dtype)
+
+    def red(vs):
+        acc = vs[0].to(torch.float64 if dtype.is_floating_point else torch.int64)
+        for v in vs[1:]:
+            v = v.to(acc.dtype)
+            acc = acc + v if func == SUM else torch.maximum(acc, v)
+        return acc.to(dtype)
+
+    kw = dict(compress_dtype=wire) if wire is not None else {}
+
+    def fn(a, r, w):
+        if op == "sendrecv":
+            s, d = a.create_buffer(count, dtype), a.create_buffer(count, dtype)
+            s.host[:] = vals(count, r)
+            req = a.send(s, count, (r + 1) % w, tag=1, run_async=True, **kw)
+            a.recv(d, count, (r - 1) % w, tag=1, **kw)
+            req.wait()
+            assert torch.equal(d.host, vals(count, (r - 1) % w))
+        elif op == "bcast":
+            b = a.create_buffer(count, dtype)
+            b.host[:] = vals(count, r)
+            a.bcast(b, count, root, **kw)
+            assert torch.equal(b.host, vals(count, root))
+        elif op == "allgather":
+            s, d = a.create_buffer(count, dtype), a.create_buffer(count * w, dtype)
+            s.host[:] = vals(count, r)
+            a.allgather(s, d, count, **kw)
+            assert torch.equal(d.host, torch.cat([vals(count, q) for q in range(w)]))
+        elif op == "reduce":
+            s, d = a.create_buffer(count, dtype), a.create_buffer(count, dtype)
+            s.host[:] = vals(count, r)
+            a.reduce(s, d, count, root, func, **kw)
+            if r == root:
+                assert torch.equal(d.host, red([vals(count, q) for q in range(w)]))
+        elif op == "allreduce":
+            s, d = a.create_buffer(count, dtype), a.create_buffer(count, dtype)
+            s.host[:] = vals(count, r)
+            a.allreduce(s, d, count, func, **kw)
+            assert torch.equal(d.host, red([vals(count, q) for q in range(w)]))
+        else:
+            s, d = a.create_buffer(count * w, dtype), a.create_buffer(count, dtype)
+            s.host[:] = vals(count * w, r)
+            a.reduce_scatter(s, d, count, func, **kw)
+            assert torch.equal(d.host, red([vals(count * w, q) for q in range(w)])[r * count:(r + 1) * count])
+    A.run_ranks(world, fn, cfg, timeout=120.0)
