@@ -734,3 +734,45 @@ def test_rank_table_helpers(tmp_path):
     [t.start() for t in ts]
     [t.join(60) for t in ts]
     assert not errs, errs
+
+
+# ------------------------------------------------------------ failure detection
+def test_receive_timeout_and_error_decoding():
+    """A recv nobody answers fails with RECEIVE_TIMEOUT_ERROR after `set_timeout`; the exception names the bits."""
+    def fn(a, r, w):
+        a.set_timeout(20000)                          # 20 ms in engine ticks (us)
+        if r == 0:
+            d = a.create_buffer(16)
+            with pytest.raises(RuntimeError, match="RECEIVE_TIMEOUT_ERROR"):
+                a.recv(d, 16, 1, tag=77)
+        a.barrier()                                   # the engine is still usable afterwards
+    A.run_ranks(2, fn, EAGER)
+
+
+def test_wait_with_timeout_and_soft_reset_drains_parked_calls():
+    """A rendezvous send without a receiver parks in the retry queue: wait(timeout) reports 'not yet', and
+    soft_reset hands the waiter NOT_READY_ERROR instead of leaving it hanging (reference fw:2249-2261)."""
+    def fn(a, r, w):
+        if r == 0:
+            big = a.create_buffer(4000)
+            req = a.send(big, 4000, 1, tag=9, run_async=True)
+            assert req.wait_for(50) is False          # still parked after 50 ms
+            assert not req.test()
+            a.impl.soft_reset()
+            assert req.wait_for(2000) is True
+            assert req.retcode() != 0
+            assert "NOT_READY" in A._C.error_to_string(req.retcode())
+    A.run_ranks(2, fn, RNDZV)
+
+
+def test_bad_arguments_are_rejected():
+    def fn(a, r, w):
+        s, d = a.create_buffer(8), a.create_buffer(8)
+        with pytest.raises(RuntimeError):
+            a.bcast(s, 8, 7)                          # root outside the communicator
+        with pytest.raises((RuntimeError, IndexError)):
+            a.allreduce(s, d, 8, SUM, comm_id=5)      # communicator never created
+        with pytest.raises((RuntimeError, IndexError, ValueError)):
+            a.copy(s, d, 64)                          # count beyond the buffers
+        a.barrier()
+    A.run_ranks(2, fn, EAGER)
