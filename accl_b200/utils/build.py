@@ -71,6 +71,9 @@ def _compile(src, with_cuda, hdr_mtime, verbose, force):
     if not force and obj.exists() and obj.stat().st_mtime > max(srcp.stat().st_mtime, hdr_mtime):
         return obj
     defs = ["-DACCL_WITH_CUDA"] if with_cuda else []
+    # opt-in code paths kept out of the default build (see docs/roadmap.md), e.g.
+    # ACCL_EXTRA_DEFINES=ACCL_EXPERIMENTAL_REDUCE_PUSH python -m accl_b200.utils.build -f
+    defs += ["-D" + d for d in os.environ.get("ACCL_EXTRA_DEFINES", "").split(",") if d]
     if src.endswith(".cu"):
         cmd = [NVCC, "-ccbin", CXX, "-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-fvisibility=hidden",
                "--expt-relaxed-constexpr", "-Xptxas", "-v" if verbose else "-O3",
@@ -121,6 +124,33 @@ def build(with_cuda=True, verbose=False, force=False, tools=True):
     return out
 
 
+def check_experimental(defines, verbose=True):
+    """Compile (do not link) every CUDA-backend source with extra -D switches into build/obj_exp: the way to
+    syntax- and resource-check code that is kept out of the default build (e.g. ACCL_EXPERIMENTAL_REDUCE_PUSH)."""
+    out = ROOT / "build" / "obj_exp"
+    out.mkdir(parents=True, exist_ok=True)
+    srcs = sorted(str(p.relative_to(CSRC)) for p in (CSRC / "src" / "cuda").glob("*.cu")) + \
+        sorted(str(p.relative_to(CSRC)) for p in (CSRC / "src" / "cuda").glob("*.cpp"))
+    dflags = ["-D" + d for d in defines] + ["-DACCL_WITH_CUDA"]
+    for src in srcs:
+        obj = out / (src.replace("/", "_") + ".o")
+        if src.endswith(".cu"):
+            cmd = [NVCC, "-ccbin", CXX, "-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+                   "-Xptxas", "-v", *dflags, *_includes(), "-c", str(CSRC / src), "-o", str(obj)]
+        else:
+            cmd = [CXX, "-std=c++17", "-O2", "-fPIC", "-Wall", "-Wno-unused-function", *dflags, *_includes(), "-c",
+                   str(CSRC / src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("experimental compile failed: " + src)
+        if verbose:
+            for line in (r.stdout + r.stderr).splitlines():
+                if "Used" in line or "spill" in line or "Compiling entry" in line or "warning" in line:
+                    print(line)
+    return out
+
+
 def build_tool(name, verbose=False):
     """Host-only tools (cclo_emu, emu_selftest) need no CUDA toolchain: g++ build into build/bin."""
     BIN.mkdir(parents=True, exist_ok=True)
@@ -154,7 +184,12 @@ if __name__ == "__main__":
     ap.add_argument("--no-tools", action="store_true")
     ap.add_argument("--sanitize", choices=["address", "thread"], help="build build/bin/<tool>_<kind> only")
     ap.add_argument("--suite", action="store_true", help="with --sanitize: build the full emu_suite instead of emu_selftest")
+    ap.add_argument("--check-define", action="append", default=[], metavar="MACRO",
+                    help="compile the CUDA backend with -DMACRO into build/obj_exp (no link): syntax / resource check")
     a = ap.parse_args()
+    if a.check_define:
+        print(check_experimental(a.check_define))
+        sys.exit(0)
     if a.sanitize:
         print(build_sanitized(a.sanitize, a.verbose, "emu_suite" if a.suite else "emu_selftest"))
         sys.exit(0)

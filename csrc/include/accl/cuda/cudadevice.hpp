@@ -127,6 +127,9 @@ private:
   RequestRegistry requests_;
   std::shared_ptr<BufferStorage> egr_area_;
   std::shared_ptr<BufferStorage> strm_area_;
+#ifdef ACCL_EXPERIMENTAL_REDUCE_PUSH
+  std::shared_ptr<BufferStorage> scr_area_; // scratch of the write-only rooted reduce (docs/roadmap.md #1)
+#endif
   friend struct CudaRequest;
   friend class Engine;
   std::unique_ptr<class Engine> engine_;

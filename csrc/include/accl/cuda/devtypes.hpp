@@ -107,6 +107,10 @@ struct DevWorld {
   uint32_t egr_slot_bytes;
   uint64_t strm_off;   // heap offset of the device-side stream FIFO (same on every rank)
   uint64_t strm_cap;   // its capacity in bytes (power of two)
+#ifdef ACCL_EXPERIMENTAL_REDUCE_PUSH
+  uint64_t scr_off;    // heap offset of the collective scratch region (same on every rank)
+  uint64_t scr_bytes;
+#endif
 };
 
 struct WorkItem {

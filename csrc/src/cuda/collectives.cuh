@@ -434,6 +434,12 @@ __device__ __forceinline__ bool all_equal(const uint64_t *v, uint32_t P) {
   return eq;
 }
 
+__device__ __forceinline__ bool all_aligned16(const uint64_t *v, uint32_t P) {
+  bool ok = true;
+  for (uint32_t q = 0; q < P; ++q) ok = ok && (v[q] & 15) == 0;
+  return ok;
+}
+
 // fill the CTA's pointer table: src[k] / dst[k] for k < P, rotated so that my
 // own buffers come first (staggers the peers each rank touches first)
 __device__ __forceinline__ void fill_table(const Ctx &c, const uint64_t *s_off0, const uint64_t *s_off2, uint64_t src_add,
@@ -602,6 +608,75 @@ __device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_o
   chan_sync(c, false, 0, 0, nullptr, nullptr);
 }
 
+#ifdef ACCL_EXPERIMENTAL_REDUCE_PUSH
+// EXPERIMENTAL (not compiled by default, not yet validated on hardware; docs/roadmap.md #1).
+// Write-only rooted reduce: the message is cut into P-1 slices (one per non-root "worker") and every CTA
+// owns a stripe of every slice, processed in chunks of CH vectors.  In step st every rank PUSHES its chunk
+// st of slice j into worker j's scratch (stage st & 1, one region per source), and worker j reduces chunk
+// st - 1 from its P-1 scratch regions plus its own operand, storing the result straight into the root's
+// buffer.  Steps run in lockstep (one chan_sync per step, as in rv_bcast_pipelined), which orders the pushes
+// of step st before their reduction in step st + 1 and the reuse of a stage after its reduction.  Every port
+// carries N bytes of posted writes in and out; nobody issues remote loads.
+// Returns the number of vectors it reduced (0: geometry does not fit, caller falls back).
+__device__ __noinline__ size_t rv_reduce_push(const Ctx &c, const uint64_t *s_off0, const uint64_t *s_off2) {
+  const WorkItem &it = c.it;
+  const uint32_t P = c.P(), me = c.r(), root = it.desc.root_src_dst, W = P - 1;
+  const size_t es = esize(it.udtype);
+  const size_t nvec = static_cast<size_t>(it.desc.count) * es / 16;
+  // scratch per heap: [stage 2][cta][source rank P][CH vectors]
+  size_t CH = c.w.scr_bytes / (static_cast<size_t>(2) * c.nctas * P * 16);
+  if (CH > 16384) CH = 16384;
+  CH &= ~static_cast<size_t>(31); // whole warps of vectors
+  if (CH < 256 || W < 2) return 0;
+  const size_t per_slice = (nvec + W - 1) / W;
+  const size_t per_cta = (per_slice + c.nctas - 1) / c.nctas;
+  const size_t steps = (per_cta + CH - 1) / CH;
+  const uint32_t j_me = (me + P - root - 1) % P; // my worker index (meaningless on the root)
+  const char *src = c.heap(c.w.rank) + s_off0[me];
+  char *root_dst = c.heap(c.g(root)) + s_off2[root];
+  auto range = [&](uint32_t j, size_t step, size_t &a, size_t &b) {
+    a = j * per_slice + static_cast<size_t>(c.cta) * per_cta + step * CH;
+    b = a + CH;
+    const size_t lim_cta = j * per_slice + (static_cast<size_t>(c.cta) + 1) * per_cta;
+    const size_t lim_slice = (j + 1) * per_slice < nvec ? (j + 1) * per_slice : nvec;
+    if (b > lim_cta) b = lim_cta;
+    if (b > lim_slice) b = lim_slice;
+  };
+  auto scr = [&](uint32_t owner_grank, size_t stage, uint32_t src_rank) -> char * {
+    return c.heap(owner_grank) + c.w.scr_off + (((stage * c.nctas + c.cta) * P + src_rank) * CH) * 16;
+  };
+  for (size_t st = 0; st <= steps; ++st) {
+    if (st < steps) {
+      // deal my chunk of every slice to the worker that owns it (my own slice stays where it is)
+      for (uint32_t k = 0; k < W; ++k) {
+        const uint32_t j = (k + static_cast<uint32_t>(c.cta)) % W; // CTAs start on different workers
+        const uint32_t q = (root + 1 + j) % P;
+        if (q == me) continue;
+        size_t a, b;
+        range(j, st, a, b);
+        if (a < b) copy_simple(scr(c.g(q), st & 1, me), src + a * 16, (b - a) * 16, 0, 1);
+      }
+    }
+    if (me != root && st >= 1) {
+      size_t a, b;
+      range(j_me, st - 1, a, b);
+      if (a < b) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          c.tab->src[0] = src + a * 16;
+          for (uint32_t k = 1; k < P; ++k) c.tab->src[k] = scr(c.w.rank, (st - 1) & 1, (me + k) % P);
+          c.tab->dst[0] = root_dst + a * 16;
+        }
+        __syncthreads();
+        reduce_dispatch(c.tab, static_cast<int>(P), 1, (b - a) * (16 / es), it.udtype, it.desc.function, 0, 1, c.err);
+      }
+    }
+    chan_sync(c, false, 0, 0, nullptr, nullptr);
+  }
+  return nvec;
+}
+#endif
+
 // reduce to root.  Small: the root pulls (or lets the switch reduce) everything.  Large
 // (P >= 3): the P-1 other ranks each reduce one slice and store it into the root's buffer,
 // so the root's inbound link carries N bytes instead of (P-1) N.
@@ -618,6 +693,13 @@ __device__ __noinline__ void rv_reduce(const Ctx &c, uint64_t *s_off0, uint64_t 
     const size_t nvec = count * es / 16;
     const bool distributed = P >= 3 && count * es >= (1u << 20) && (s_off2[root] & 15) == 0;
     size_t done = 0;
+#ifdef ACCL_EXPERIMENTAL_REDUCE_PUSH
+    // all ranks take the same decision: it only depends on the call and on the (identical) geometry
+    if (distributed && count * es >= (8u << 20) && all_aligned16(s_off0, P)) done = rv_reduce_push(c, s_off0, s_off2) * 16 / es;
+    if (done) {
+      // handled above; the sub-vector tail (if any) is reduced by the root below
+    } else
+#endif
     if (distributed) {
       if (me != root) {
         const uint32_t j = (me + P - root - 1) % P; // my index among the P-1 workers

@@ -208,6 +208,15 @@ CudaDevice::CudaDevice(std::shared_ptr<Oob> oob, const CudaConfig &cfg) : oob_(s
   strm_area_ = allocate(STREAM_FIFO_BYTES, bufferKind::p2p);
   world_.strm_off = strm_area_->device_addr();
   world_.strm_cap = STREAM_FIFO_BYTES;
+#ifdef ACCL_EXPERIMENTAL_REDUCE_PUSH
+  {
+    // second allocation: same offset in every heap as well
+    const size_t scr = std::min<size_t>(64u << 20, heap_->bytes() / 8);
+    scr_area_ = allocate(scr, bufferKind::p2p);
+    world_.scr_off = scr_area_->device_addr();
+    world_.scr_bytes = scr;
+  }
+#endif
   preload_engine_kernels();
   preload_gemm_rs_kernels();
   preload_vadd_kernels();
