@@ -93,6 +93,13 @@ struct Ctrl {
   unsigned long long strm_reserve; // bytes reserved by producers (local kernels or peers doing stream_put)
   uint32_t strm_err;               // sticky error bits raised by stream helper kernels
   uint32_t strm_pad;
+#ifdef ACCL_PHASE_TIMING
+  // opt-in instrumentation (channel 0 only): where a call's time goes.  Read with CudaDevice::debug_state().
+  unsigned long long dbg_calls;      // calls executed
+  unsigned long long dbg_kernel_ns;  // sum of kernel body durations (run_work entry -> exit)
+  unsigned long long dbg_sync_ns;    // of which spent inside chan_sync / pair_sync (flag round trips)
+  unsigned long long dbg_syncs;      // number of meetings
+#endif
 };
 static_assert(sizeof(Ctrl) <= CTRL_BYTES / 2, "control block too large");
 

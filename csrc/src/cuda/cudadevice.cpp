@@ -283,6 +283,14 @@ std::string CudaDevice::debug_state() {
         << " sig=" << c->egr_sig[ch][p] << "]";
     o << "\n";
   }
+#ifdef ACCL_PHASE_TIMING
+  o << " phase timing (channel 0): calls=" << c->dbg_calls << " kernel_ns=" << c->dbg_kernel_ns << " sync_ns=" << c->dbg_sync_ns
+    << " syncs=" << c->dbg_syncs;
+  if (c->dbg_calls)
+    o << "  per call: kernel " << c->dbg_kernel_ns / c->dbg_calls << " ns, in meetings " << c->dbg_sync_ns / c->dbg_calls
+      << " ns over " << static_cast<double>(c->dbg_syncs) / static_cast<double>(c->dbg_calls) << " meetings";
+  o << "\n";
+#endif
   return o.str();
 }
 

@@ -277,6 +277,13 @@ __global__ void __launch_bounds__(k::BLOCK) k_call(DevWorld w, WorkItem it, Host
   __syncthreads();
   k::run_work(w, it, blockIdx.x, gridDim.x, &s_err);
   __syncthreads();
+#ifdef ACCL_PHASE_TIMING
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    Ctrl *dc = reinterpret_cast<Ctrl *>(w.window + static_cast<uint64_t>(w.rank) * w.heap_bytes);
+    dc->dbg_calls += 1;
+    dc->dbg_kernel_ns += dev::globaltimer_ns() - t0;
+  }
+#endif
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) { // stream helper kernels that ran before this call report through it
       Ctrl *mc = reinterpret_cast<Ctrl *>(w.window + static_cast<uint64_t>(w.rank) * w.heap_bytes);

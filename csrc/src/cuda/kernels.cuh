@@ -69,6 +69,9 @@ __device__ __forceinline__ bool wait_ge(const uint32_t *p, uint32_t target, cons
 __device__ __forceinline__ void chan_sync(const Ctx &c, bool exchange, uint64_t my_off0, uint64_t my_off2,
                                           uint64_t *s_off0, uint64_t *s_off2) {
   __syncthreads(); // every thread's prior writes happen-before the release below
+#ifdef ACCL_PHASE_TIMING
+  const unsigned long long dbg_t0 = (c.cta == 0 && threadIdx.x == 0) ? globaltimer_ns() : 0;
+#endif
   const uint32_t t = threadIdx.x;
   const uint32_t ch = static_cast<uint32_t>(c.cta);
   if (t < c.P()) {
@@ -100,6 +103,12 @@ __device__ __forceinline__ void chan_sync(const Ctx &c, bool exchange, uint64_t 
     }
   }
   __syncthreads();
+#ifdef ACCL_PHASE_TIMING
+  if (c.cta == 0 && threadIdx.x == 0) {
+    c.me->dbg_sync_ns += globaltimer_ns() - dbg_t0;
+    c.me->dbg_syncs += 1;
+  }
+#endif
 }
 
 // pairwise variant for send/recv: only (me, peer) take part; kinds differ by design
