@@ -9,7 +9,27 @@ import os
 import sys
 
 
+def _load_variant(name):
+    """ACCL_VARIANT=<name>: use the extension of build/variants/<name> (python -m accl_b200.utils.build --variant
+    <name> --define MACRO ...) instead of the default one — same Python sources, different compile-time switches."""
+    import glob
+    import importlib.machinery
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hits = glob.glob(os.path.join(root, "build", "variants", name, "accl_b200", "_C*.so"))
+    if not hits:
+        raise ImportError(f"ACCL_VARIANT={name}: no extension under build/variants/{name}; build it first")
+    loader = importlib.machinery.ExtensionFileLoader("accl_b200._C", hits[0])
+    spec = importlib.util.spec_from_loader("accl_b200._C", loader, origin=hits[0])
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    mod.__file__ = hits[0]
+    return mod
+
+
 def _load_native():
+    if os.environ.get("ACCL_VARIANT"):
+        return _load_variant(os.environ["ACCL_VARIANT"])
     try:
         return importlib.import_module("accl_b200._C")
     except ImportError as first:
@@ -24,7 +44,7 @@ def _load_native():
 
 
 _C = _load_native()
-sys.modules.setdefault("accl_b200._C", _C)
+sys.modules["accl_b200._C"] = _C
 
 from .core import (Accl, Buffer, BufferKind, DataType, GLOBAL_COMM, MAX, ReduceFunction, SUM, TAG_ANY,  # noqa: E402
                    cuda_rank, cuda_world, emulator_world, remote_rank, run_cuda_ranks, run_ranks, socket_rank)

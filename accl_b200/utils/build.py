@@ -89,7 +89,7 @@ def ext_path():
     return ROOT / "accl_b200" / ("_C" + sysconfig.get_config_var("EXT_SUFFIX"))
 
 
-def build(with_cuda=True, verbose=False, force=False, tools=True):
+def build(with_cuda=True, verbose=False, force=False, tools=True, out_path=None):
     OBJ.mkdir(parents=True, exist_ok=True)
     BIN.mkdir(parents=True, exist_ok=True)
     cu = sorted(str(p.relative_to(CSRC)) for p in (CSRC / "src" / "cuda").glob("*.cu"))
@@ -100,7 +100,7 @@ def build(with_cuda=True, verbose=False, force=False, tools=True):
     hdr = _newest_header_mtime()
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         objs = list(ex.map(lambda s: _compile(s, with_cuda, hdr, verbose, force), srcs))
-    out = ext_path()
+    out = Path(out_path) if out_path else ext_path()
     if force or not out.exists() or any(o.stat().st_mtime > out.stat().st_mtime for o in objs):
         if with_cuda:
             link = [NVCC, "-ccbin", CXX, "-shared", *ARCH, "-cudart", "static", "-Xcompiler", "-fPIC",
@@ -151,6 +151,31 @@ def check_experimental(defines, verbose=True):
     return out
 
 
+def build_variant(name, defines, verbose=False):
+    """A second, self-contained copy of the package built with extra -D switches:
+    build/variants/<name>/accl_b200 (python sources copied, own _C extension, own object directory).
+    `PYTHONPATH=build/variants/<name> python ...` then runs that build next to the default one — one GPU
+    session can compare both (e.g. ACCL_PHASE_TIMING, ACCL_EXPERIMENTAL_REDUCE_PUSH)."""
+    import shutil
+    global OBJ
+    pkg = ROOT / "build" / "variants" / name / "accl_b200"
+    if pkg.exists():
+        shutil.rmtree(pkg)
+    shutil.copytree(ROOT / "accl_b200", pkg, ignore=shutil.ignore_patterns("__pycache__", "*.so"))
+    saved_obj, saved_env = OBJ, os.environ.get("ACCL_EXTRA_DEFINES")
+    OBJ = ROOT / "build" / ("obj_" + name)
+    os.environ["ACCL_EXTRA_DEFINES"] = ",".join(defines)
+    try:
+        out = build(with_cuda=True, verbose=verbose, force=False, tools=False, out_path=pkg / ext_path().name)
+    finally:
+        OBJ = saved_obj
+        if saved_env is None:
+            os.environ.pop("ACCL_EXTRA_DEFINES", None)
+        else:
+            os.environ["ACCL_EXTRA_DEFINES"] = saved_env
+    return out
+
+
 def build_tool(name, verbose=False):
     """Host-only tools (cclo_emu, emu_selftest) need no CUDA toolchain: g++ build into build/bin."""
     BIN.mkdir(parents=True, exist_ok=True)
@@ -184,9 +209,14 @@ if __name__ == "__main__":
     ap.add_argument("--no-tools", action="store_true")
     ap.add_argument("--sanitize", choices=["address", "thread"], help="build build/bin/<tool>_<kind> only")
     ap.add_argument("--suite", action="store_true", help="with --sanitize: build the full emu_suite instead of emu_selftest")
+    ap.add_argument("--variant", metavar="NAME", help="with --define: build build/variants/NAME/accl_b200 with the extra macros")
+    ap.add_argument("--define", action="append", default=[], metavar="MACRO")
     ap.add_argument("--check-define", action="append", default=[], metavar="MACRO",
                     help="compile the CUDA backend with -DMACRO into build/obj_exp (no link): syntax / resource check")
     a = ap.parse_args()
+    if a.variant:
+        print(build_variant(a.variant, a.define, a.verbose))
+        sys.exit(0)
     if a.check_define:
         print(check_experimental(a.check_define))
         sys.exit(0)
