@@ -343,6 +343,21 @@ def test_large_reduce_is_distributed_over_workers():
     run(3, fn, RNDZV)
 
 
+@pytest.mark.parametrize("func", [SUM, MAX])
+def test_large_reduce_12mib_chunked(func):
+    """12 MiB + tail: the size class of the chunked rooted-reduce schemes (docs/roadmap.md #1; with the
+    ACCL_EXPERIMENTAL_REDUCE_PUSH build this is the write-only path, otherwise the distributed pull)."""
+    n = (3 << 20) + 5
+
+    def fn(a, r, w):
+        s, d = a.create_buffer(n), a.create_buffer(n)
+        s.host[:] = data(n, r, salt=3)
+        a.reduce(s, d, n, 1, func)
+        if r == 1:
+            assert close(d.host, ref_reduce(w, n, func, salt=3), 1e-5, 1e-4)
+    A.run_cuda_ranks(devices(3), fn, RNDZV, heap_mb=256, max_ctas=8)
+
+
 @pytest.mark.multigpu
 @pytest.mark.skipif(NGPU < 3, reason="pipelined NVLS broadcast needs >= 3 GPUs")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
