@@ -93,6 +93,12 @@ struct Ctrl {
   unsigned long long strm_reserve; // bytes reserved by producers (local kernels or peers doing stream_put)
   uint32_t strm_err;               // sticky error bits raised by stream helper kernels
   uint32_t strm_pad;
+#ifdef ACCL_EXPERIMENTAL_BCAST_FLAGS
+  // one-way "chunk landed" counters of the flag-driven pipelined broadcast (docs/roadmap.md #2)
+  uint32_t step_sig[MAX_CH][ACCL_MAX_RANKS];  // written by peers: chunks src has delivered to me on this channel
+  uint32_t step_seen[MAX_CH][ACCL_MAX_RANKS]; // local: how many of them earlier calls already consumed
+  uint32_t step_sent[MAX_CH][ACCL_MAX_RANKS]; // local: chunks I have delivered to dst
+#endif
 #ifdef ACCL_PHASE_TIMING
   // opt-in instrumentation (channel 0 only): where a call's time goes.  Read with CudaDevice::debug_state().
   unsigned long long dbg_calls;      // calls executed

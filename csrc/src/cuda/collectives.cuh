@@ -540,6 +540,9 @@ __device__ __noinline__ void rv_reduce_scatter(const Ctx &c, uint64_t *s_off0, u
 }
 
 __device__ __noinline__ void rv_bcast_pipelined(const Ctx &c, const uint64_t *s_off);
+#ifdef ACCL_EXPERIMENTAL_BCAST_FLAGS
+__device__ __noinline__ void rv_bcast_flags(const Ctx &c, const uint64_t *s_off);
+#endif
 
 // push-style data movement shared by allgather / bcast / scatter / gather / alltoall
 __device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_off0, uint64_t *s_off2) {
@@ -568,7 +571,11 @@ __device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_o
       break;
     case EP_BCAST:
       if (bcast_pipelined) {
+#ifdef ACCL_EXPERIMENTAL_BCAST_FLAGS
+        rv_bcast_flags(c, s_off2);
+#else
         rv_bcast_pipelined(c, s_off2);
+#endif
       } else if (me == root) {
         if (mc_ok) {
           // the multicast store also rewrites the root's own copy with identical bytes
@@ -783,6 +790,90 @@ __device__ __noinline__ void rv_bcast_pipelined(const Ctx &c, const uint64_t *s_
     chan_sync(c, false, 0, 0, nullptr, nullptr);
   }
 }
+
+#ifdef ACCL_EXPERIMENTAL_BCAST_FLAGS
+// EXPERIMENTAL (not compiled by default, not yet validated on hardware; docs/roadmap.md #2).
+// Same deal-and-forward schedule as rv_bcast_pipelined, driven by one-way flags instead of a meeting per
+// step: after the stores of a chunk the producer raises a per-(channel, source) counter at the consumer
+// (st.release.sys); the consumer waits for the count it needs (ld.acquire.sys).  The root never waits, a
+// worker waits for the root's chunk before forwarding it and, at the end, for every other worker to have
+// delivered all of its chunks.  Counters are monotonic across calls (step_seen / step_sent), every
+// (producer, consumer, step) signals exactly once whether or not the chunk is empty.
+__device__ __noinline__ void rv_bcast_flags(const Ctx &c, const uint64_t *s_off) {
+  const WorkItem &it = c.it;
+  const uint32_t P = c.P(), me = c.r(), root = it.desc.root_src_dst;
+  const size_t nvec = static_cast<size_t>(it.desc.count) * esize(it.udtype) / 16;
+  const uint32_t W = P - 1, ch = static_cast<uint32_t>(c.cta);
+  const size_t per_slice = (nvec + W - 1) / W;
+  const size_t per_cta = (per_slice + c.nctas - 1) / c.nctas;
+  size_t CH = per_cta / 8;
+  CH = CH < 2048 ? 2048 : (CH > 16384 ? 16384 : CH);
+  const uint32_t steps = static_cast<uint32_t>((per_cta + CH - 1) / CH);
+  const uint32_t j_me = (me + P - root - 1) % P;
+  const char *src = c.heap(c.w.rank) + s_off[me];
+  auto range = [&](uint32_t j, size_t step, size_t &a, size_t &b) {
+    a = j * per_slice + static_cast<size_t>(c.cta) * per_cta + step * CH;
+    b = a + CH;
+    const size_t lim_cta = j * per_slice + (static_cast<size_t>(c.cta) + 1) * per_cta;
+    const size_t lim_slice = (j + 1) * per_slice < nvec ? (j + 1) * per_slice : nvec;
+    if (b > lim_cta) b = lim_cta;
+    if (b > lim_slice) b = lim_slice;
+  };
+  // all stores of this CTA to rank q's buffer are done: tell q (one thread, after a CTA barrier)
+  auto signal = [&](uint32_t q) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t gq = c.g(q);
+      const uint32_t v = c.me->step_sent[ch][gq] + 1;
+      c.me->step_sent[ch][gq] = v;
+      st_release_sys(&c.ctrl(gq)->step_sig[ch][c.w.rank], v);
+    }
+  };
+  // wait until rank q has delivered `n` chunks of this call to me
+  auto await = [&](uint32_t q, uint32_t n) {
+    if (threadIdx.x == 0) wait_ge(&c.me->step_sig[ch][c.g(q)], c.me->step_seen[ch][c.g(q)] + n, c, RECEIVE_TIMEOUT_ERROR);
+    __syncthreads();
+  };
+  if (me == root) {
+    for (uint32_t st = 0; st < steps; ++st)
+      for (uint32_t k = 0; k < W; ++k) {
+        const uint32_t j = (k + ch) % W; // CTAs start on different workers
+        const uint32_t q = (root + 1 + j) % P;
+        size_t a, b;
+        range(j, st, a, b);
+        if (a < b) copy_simple(c.heap(c.g(q)) + s_off[q] + a * 16, src + a * 16, (b - a) * 16, 0, 1);
+        signal(q);
+      }
+  } else {
+    for (uint32_t st = 0; st < steps; ++st) {
+      await(root, st + 1);
+      size_t a, b;
+      range(j_me, st, a, b);
+      if (a < b && W >= 2) {
+        if (threadIdx.x == 0) {
+          int nd = 0;
+          for (uint32_t k = 1; k < W; ++k) {
+            const uint32_t q = (root + 1 + (j_me + k) % W) % P;
+            c.tab->dst[nd++] = c.heap(c.g(q)) + s_off[q] + a * 16;
+          }
+          c.tab->src[0] = src + a * 16; // what the root stored here
+        }
+        __syncthreads();
+        copy_dispatch(c.tab, static_cast<int>(W) - 1, (b - a) * 16, 0, 1);
+      }
+      for (uint32_t k = 1; k < W; ++k) signal((root + 1 + (j_me + k) % W) % P);
+    }
+    // the other workers' slices: complete once each of them has forwarded all of its chunks to me
+    for (uint32_t k = 1; k < W; ++k) await((root + 1 + (j_me + k) % W) % P, steps);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      c.me->step_seen[ch][c.g(root)] += steps;
+      for (uint32_t k = 1; k < W; ++k) c.me->step_seen[ch][c.g((root + 1 + (j_me + k) % W) % P)] += steps;
+    }
+    __syncthreads();
+  }
+}
+#endif
 
 // rendezvous send / recv: a pair of ranks meets on the pads, the receiver
 // announces its buffer, the sender stores straight into it

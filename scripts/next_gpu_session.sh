@@ -2,6 +2,7 @@
 # First GPU session of the next round (docs/roadmap.md): build the variants on the build host first:
 #   python -m accl_b200.utils.build --variant timing --define ACCL_PHASE_TIMING
 #   python -m accl_b200.utils.build --variant rpush  --define ACCL_EXPERIMENTAL_REDUCE_PUSH
+#   python -m accl_b200.utils.build --variant bflags --define ACCL_EXPERIMENTAL_BCAST_FLAGS
 # then: gpurun --gpus 4 -- 'bash scripts/next_gpu_session.sh 4'
 N=${1:-4}
 mkdir -p gpurun_out
@@ -12,7 +13,10 @@ ACCL_VARIANT=timing timeout 200 $TR --master-port 29571 scripts/phase_timing.py 
 echo "--- 2. write-only reduce (experimental build): correctness, then the rooted sweep"
 ACCL_VARIANT=rpush timeout 200 python -m pytest tests/test_cuda.py -q --timeout 150 -k "large_reduce or rooted" 2>&1 | tail -2
 ACCL_VARIANT=rpush timeout 300 $TR --master-port 29573 bench/sweep.py --ops reduce --dtype bfloat16 --min-log2 23 --max-log2 28 --step 1 --out gpurun_out/sweep_${N}gpu_reduce_push.csv 2>/dev/null | grep '^{' | cut -c1-220
+echo "--- 2b. flag-driven pipelined bcast (experimental build)"
+ACCL_VARIANT=bflags timeout 200 python -m pytest tests/test_cuda.py -q --timeout 150 -k "large_bcast" 2>&1 | tail -2
+ACCL_VARIANT=bflags timeout 300 $TR --master-port 29574 bench/sweep.py --ops bcast --dtype bfloat16 --min-log2 27 --max-log2 30 --step 1 --out gpurun_out/sweep_${N}gpu_bcast_flags.csv 2>/dev/null | grep '^{' | cut -c1-220
 echo "--- 3. default build: same reduce sizes for comparison, vadd plugin timing, fuzz"
-timeout 300 $TR --master-port 29575 bench/sweep.py --ops reduce --dtype bfloat16 --min-log2 23 --max-log2 28 --step 1 --out gpurun_out/sweep_${N}gpu_reduce_default.csv 2>/dev/null | grep '^{' | cut -c1-220
+timeout 300 $TR --master-port 29575 bench/sweep.py --ops reduce,bcast --dtype bfloat16 --min-log2 23 --max-log2 30 --step 1 --out gpurun_out/sweep_${N}gpu_rooted_default.csv 2>/dev/null | grep '^{' | cut -c1-220
 timeout 300 $TR --master-port 29577 bench/vadd.py --min-log2 12 --max-log2 26 --step 2 --out gpurun_out/vadd_${N}gpu.jsonl 2>/dev/null | cut -c1-200
 timeout 300 python scripts/gpu_fuzz.py 150 $N 2>&1 | tail -3
