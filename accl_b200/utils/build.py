@@ -108,6 +108,17 @@ def build(with_cuda=True, verbose=False, force=False, tools=True, out_path=None)
         else:
             link = [CXX, "-shared", "-fPIC", *[str(o) for o in objs], "-o", str(out), "-lpthread"]
         _run(link, verbose)
+    if tools:
+        # the C++ library on its own (no Python): build/lib/libaccl.a + headers under csrc/include.  Static,
+        # because the objects are compiled with hidden visibility for the Python extension; link with
+        #   g++ app.cpp -Icsrc/include build/lib/libaccl.a [libcudart_static.a] -lpthread -ldl -lrt
+        lib = ROOT / "build" / "lib" / "libaccl.a"
+        lib.parent.mkdir(parents=True, exist_ok=True)
+        core_objs = [o for o, s_ in zip(objs, srcs) if s_ != BINDING and "bind_" not in s_]
+        if force or not lib.exists() or any(o.stat().st_mtime > lib.stat().st_mtime for o in core_objs):
+            if lib.exists():
+                lib.unlink()
+            _run(["ar", "rcs", str(lib), *[str(o) for o in core_objs]], verbose)
     if tools and not with_cuda:
         for name in ("cclo_emu", "emu_selftest", "emu_suite", "emu_bench"):
             build_tool(name, verbose)

@@ -101,3 +101,24 @@ def test_data_parallel_mlp_trains(zero):
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][0]
     out = json.loads(line)
     assert out["ok"] and out["replicas_identical"] and out["loss_last"] < out["loss_first"]
+
+
+def test_cpp_example_links_against_the_static_library(tmp_path):
+    """examples/cpp/allreduce_emulator.cpp against build/lib/libaccl.a: the path a C++ user of the reference's
+    driver takes (no Python anywhere)."""
+    from accl_b200.utils import build as b
+    lib = os.path.join(ROOT, "build", "lib", "libaccl.a")
+    if not os.path.exists(lib):
+        pytest.skip("static library not built (python -m accl_b200.utils.build)")
+    exe = str(tmp_path / "allreduce_emulator")
+    cmd = [b.CXX, "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "csrc", "include"),
+           os.path.join(ROOT, "examples", "cpp", "allreduce_emulator.cpp"), lib]
+    cudart = "/usr/local/cuda/lib64/libcudart_static.a"
+    import accl_b200 as A
+    if A._C.with_cuda and os.path.exists(cudart):
+        cmd.append(cudart)
+    cmd += ["-lpthread", "-ldl", "-lrt", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "all ranks ok" in r.stdout, r.stdout + r.stderr
