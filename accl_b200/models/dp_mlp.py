@@ -11,7 +11,6 @@ that the loss went down, and prints one JSON line on rank 0.
 """
 import argparse
 import json
-import os
 
 import torch
 

@@ -24,7 +24,6 @@ import os
 import subprocess
 import sys
 import threading
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
