@@ -180,3 +180,58 @@ def test_dtypes_and_wire_compression(op, world, count, root, func, dtype, wire, 
             a.reduce_scatter(s, d, count, func, **kw)
             assert torch.equal(d.host, red([vals(count * w, q) for q in range(w)])[r * count:(r + 1) * count])
     A.run_ranks(world, fn, cfg, timeout=120.0)
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(world=st.integers(3, 5), data_=st.data(), op=st.sampled_from(["allreduce", "bcast", "allgather", "reduce_scatter"]),
+       count=st.integers(1, 1200), func=st.sampled_from([SUM, MAX]), cfg=geometry(), salt=st.integers(0, 100))
+def test_subcommunicators(world, data_, op, count, func, cfg, salt):
+    """A random subset of the ranks forms a communicator and runs a collective while the others stay out; then
+    everybody meets on the global communicator again (independent sequence spaces, reference test.cpp:701-832)."""
+    members = sorted(data_.draw(st.sets(st.integers(0, world - 1), min_size=2, max_size=world)))
+    root = data_.draw(st.integers(0, len(members) - 1))
+    if cfg["max_egr_size"] >= (1 << 20):
+        cfg = dict(cfg, egr_rx_buf_size=4096, n_egr_rx_bufs=32)
+        count = min(count, 1000)
+
+    def fn(a, r, w):
+        if r in members:
+            ranks = [a.get_comm_group(0)[m] for m in members]
+            me = members.index(r)
+            comm = a.create_communicator(ranks, me)
+            n = len(members)
+            if op == "allreduce":
+                s, d = a.create_buffer(count), a.create_buffer(count)
+                s.host[:] = data(count, r, salt)
+                a.allreduce(s, d, count, func, comm_id=comm)
+                vs = [data(count, m, salt) for m in members]
+                exp = vs[0].clone()
+                for v in vs[1:]:
+                    exp = exp + v if func == SUM else torch.maximum(exp, v)
+                assert torch.equal(d.host, exp)
+            elif op == "bcast":
+                b = a.create_buffer(count)
+                b.host[:] = data(count, r, salt)
+                a.bcast(b, count, root, comm_id=comm)
+                assert torch.equal(b.host, data(count, members[root], salt))
+            elif op == "allgather":
+                s, d = a.create_buffer(count), a.create_buffer(count * n)
+                s.host[:] = data(count, r, salt)
+                a.allgather(s, d, count, comm_id=comm)
+                assert torch.equal(d.host, torch.cat([data(count, m, salt) for m in members]))
+            else:
+                s, d = a.create_buffer(count * n), a.create_buffer(count)
+                s.host[:] = data(count * n, r, salt)
+                a.reduce_scatter(s, d, count, func, comm_id=comm)
+                vs = [data(count * n, m, salt) for m in members]
+                exp = vs[0].clone()
+                for v in vs[1:]:
+                    exp = exp + v if func == SUM else torch.maximum(exp, v)
+                assert torch.equal(d.host, exp[me * count:(me + 1) * count])
+        # the global communicator is unaffected
+        t = a.create_buffer(8)
+        t.host[:] = float(r)
+        u = a.create_buffer(8)
+        a.allreduce(t, u, 8, SUM)
+        assert torch.all(u.host == sum(range(w)))
+    A.run_ranks(world, fn, cfg, timeout=120.0)
