@@ -105,6 +105,8 @@ struct Ctrl {
   unsigned long long dbg_kernel_ns;  // sum of kernel body durations (run_work entry -> exit)
   unsigned long long dbg_sync_ns;    // of which spent inside chan_sync / pair_sync (flag round trips)
   unsigned long long dbg_syncs;      // number of meetings
+  unsigned long long dbg_wait_ns;    // flag waits of any kind (wait_ge), summed over the waiting threads of channel 0
+  unsigned long long dbg_waits;      // number of such waits
 #endif
 };
 static_assert(sizeof(Ctrl) <= CTRL_BYTES / 2, "control block too large");

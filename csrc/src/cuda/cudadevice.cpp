@@ -285,10 +285,12 @@ std::string CudaDevice::debug_state() {
   }
 #ifdef ACCL_PHASE_TIMING
   o << " phase timing (channel 0): calls=" << c->dbg_calls << " kernel_ns=" << c->dbg_kernel_ns << " sync_ns=" << c->dbg_sync_ns
-    << " syncs=" << c->dbg_syncs;
+    << " syncs=" << c->dbg_syncs << " wait_ns=" << c->dbg_wait_ns << " waits=" << c->dbg_waits;
   if (c->dbg_calls)
     o << "  per call: kernel " << c->dbg_kernel_ns / c->dbg_calls << " ns, in meetings " << c->dbg_sync_ns / c->dbg_calls
-      << " ns over " << static_cast<double>(c->dbg_syncs) / static_cast<double>(c->dbg_calls) << " meetings";
+      << " ns over " << static_cast<double>(c->dbg_syncs) / static_cast<double>(c->dbg_calls) << " meetings; flag waits "
+      << c->dbg_wait_ns / c->dbg_calls << " thread-ns in " << static_cast<double>(c->dbg_waits) / static_cast<double>(c->dbg_calls)
+      << " waits";
   o << "\n";
 #endif
   return o.str();

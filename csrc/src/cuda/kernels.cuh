@@ -47,6 +47,19 @@ struct Ctx {
 __device__ __forceinline__ bool wait_ge(const uint32_t *p, uint32_t target, const Ctx &c, uint32_t errbit) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
+#ifdef ACCL_PHASE_TIMING
+  struct WaitTimer {
+    const Ctx &c;
+    unsigned long long t;
+    __device__ explicit WaitTimer(const Ctx &c_) : c(c_), t(c_.cta == 0 ? globaltimer_ns() : 0) {}
+    __device__ ~WaitTimer() {
+      if (c.cta == 0) {
+        atomicAdd(&c.me->dbg_wait_ns, globaltimer_ns() - t);
+        atomicAdd(&c.me->dbg_waits, 1ull);
+      }
+    }
+  } wait_timer(c);
+#endif
   while (static_cast<int32_t>(ld_acquire_sys(p) - target) < 0) {
     ++spins;
     if (spins > 32) nanosleep(spins > 4096 ? 256 : 32);

@@ -18,7 +18,7 @@ import accl_b200 as A  # noqa: E402
 
 
 def counters(acc):
-    m = re.search(r"calls=(\d+) kernel_ns=(\d+) sync_ns=(\d+) syncs=(\d+)", acc.cuda_debug_state())
+    m = re.search(r"calls=(\d+) kernel_ns=(\d+) sync_ns=(\d+) syncs=(\d+) wait_ns=(\d+) waits=(\d+)", acc.cuda_debug_state())
     return tuple(int(x) for x in m.groups()) if m else None
 
 
@@ -63,7 +63,8 @@ def main():
             if c0 and c1 and c1[0] > c0[0]:
                 calls = c1[0] - c0[0]
                 line += (f"  body {(c1[1] - c0[1]) / calls / 1e3:7.1f} us  in meetings {(c1[2] - c0[2]) / calls / 1e3:7.1f} us"
-                         f" ({(c1[3] - c0[3]) / calls:.1f} per call)")
+                         f" ({(c1[3] - c0[3]) / calls:.1f} per call)"
+                         f"  flag waits {(c1[4] - c0[4]) / max(c1[5] - c0[5], 1) / 1e3:6.2f} us avg x {(c1[5] - c0[5]) / calls:.1f}")
             if rank == 0:
                 print(line, flush=True)
     if world > 1:
