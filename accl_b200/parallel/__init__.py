@@ -14,6 +14,8 @@ them on a B200 node:
 * `RowParallelLinear`    TP row-parallel linear whose GEMM epilogue IS the reduce-scatter
                          (tcgen05 plugin), sequence-parallel output
 * `ring_exchange`        neighbour send/recv step for context-parallel / ring-attention schedules
+* `process_group`        `torch.distributed` backend "accl" (import accl_b200.parallel.process_group): the standard
+                         ProcessGroup interface incl. DistributedDataParallel on top of this library
 * `strategies`           ZeRO-1 optimizer step, column-parallel linear, pipeline hand-off, MoE dispatch / combine,
                          Ulysses sequence <-> head re-sharding (accl_b200/parallel/strategies.py)
 """
