@@ -3,8 +3,14 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, torch.distributed as dist
 import accl_b200.parallel.process_group  # noqa
+import accl_b200 as A  # noqa: E402
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-dist.init_process_group("accl", init_method=f"tcp://127.0.0.1:{os.environ['PG_PORT']}", rank=rank, world_size=world)
+use_cuda = torch.cuda.is_available() and A._C.with_cuda and A._C.cuda_driver_available()
+if use_cuda:  # same choice init_from_env makes inside the backend; then every tensor lives on this rank's GPU
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    torch.set_default_device(torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+port = os.environ.get("PG_PORT") or str(int(os.environ.get("MASTER_PORT", 29500)) + 7)
+dist.init_process_group("accl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
 t = torch.full((1000,), float(rank + 1))
 dist.all_reduce(t)
 assert torch.all(t == world * (world + 1) / 2), t[:4]
@@ -27,7 +33,7 @@ dist.barrier()
 torch.manual_seed(0)
 model = torch.nn.Linear(8, 4)
 ddp = torch.nn.parallel.DistributedDataParallel(model)
-xs = torch.randn(16, 8, generator=torch.Generator().manual_seed(rank))
+xs = torch.randn(16, 8, generator=torch.Generator(device="cpu").manual_seed(rank), device="cpu").to(model.weight.device)
 ddp(xs).sum().backward()
 g = model.weight.grad.clone()
 chk = g.clone(); dist.all_reduce(chk, op=dist.ReduceOp.MAX)
