@@ -471,6 +471,26 @@ __device__ __noinline__ void rv_allreduce(const Ctx &c, uint64_t *s_off0, uint64
     const size_t v1 = v0 + shard < nvec ? v0 + shard : nvec;
     const NvOp nop = nvls_op(dt, it.desc.function);
     const bool sym = all_equal(s_off0, P) && all_equal(s_off2, P) && (s_off0[0] & 15) == 0 && (s_off2[0] & 15) == 0;
+#ifdef ACCL_EXPERIMENTAL_HYBRID_AR
+    // EXPERIMENTAL (compiled out by default, not yet validated on hardware; docs/roadmap.md #5b): the switch
+    // serves multimem.ld_reduce at ~540 GB/s per port while the links carry ~770: give ACCL_HYBRID_P2P_16THS / 16
+    // of my shard (and of the channels) to the peer two-shot body so both limits are used at once.
+#ifndef ACCL_HYBRID_P2P_16THS
+#define ACCL_HYBRID_P2P_16THS 3
+#endif
+    if ((it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && nop != NvOp::none && sym && c.nctas >= 16 && v1 - v0 >= (1u << 16)) {
+      const int n_p2p = c.nctas * ACCL_HYBRID_P2P_16THS / 16 > 0 ? c.nctas * ACCL_HYBRID_P2P_16THS / 16 : 1;
+      const int n_nv = c.nctas - n_p2p;
+      const size_t vm = v1 - (v1 - v0) * ACCL_HYBRID_P2P_16THS / 16;
+      if (c.cta < n_nv) {
+        nvls_reduce_dispatch<true>(nop, c.w.mc + s_off0[0], c.w.mc + s_off2[0], v0, vm, c.cta, n_nv);
+      } else {
+        fill_table(c, s_off0, s_off2, vm * 16, vm * 16, true);
+        reduce_dispatch(c.tab, static_cast<int>(P), static_cast<int>(P), (v1 - vm) * per_vec, dt, it.desc.function, c.cta - n_nv,
+                        n_p2p, c.err);
+      }
+    } else
+#endif
     if ((it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && nop != NvOp::none && sym) {
       nvls_reduce_dispatch<true>(nop, c.w.mc + s_off0[0], c.w.mc + s_off2[0], v0, v1, c.cta, c.nctas);
     } else {
