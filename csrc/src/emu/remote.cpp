@@ -89,6 +89,10 @@ void EngineServer::serve() {
   for (;;) {
     Frame f;
     if (!rx_all(fd, &f, sizeof(f))) break; // driver disconnected
+    if (f.len > (256u << 20)) {            // not one of ours (the driver chunks at 64 MiB): drop the connection
+      ACCL_ERROR_LOG("EngineServer: frame of " << f.len << " bytes refused");
+      break;
+    }
     payload.resize(f.len);
     if (f.len && !rx_all(fd, payload.data(), f.len)) break;
     Frame r;

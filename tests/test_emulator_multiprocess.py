@@ -135,3 +135,37 @@ def test_torch_distributed_backend(world):
                        text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count(": ok") == world
+
+
+def test_engine_process_survives_garbage_on_the_control_port():
+    """A stray client sending a malformed frame must not crash or wedge the engine process: unknown request
+    types are answered with an error reply, an absurd length closes the connection and the process exits cleanly."""
+    import socket
+    import struct
+    from accl_b200.models.emulator import spawn_engines
+    procs, base = spawn_engines(1, mem_mb=16, stderr=subprocess.DEVNULL)
+    try:
+        s = None
+        for _ in range(200):
+            try:
+                s = socket.create_connection(("127.0.0.1", base + 1000), timeout=5)
+                break
+            except OSError:
+                import time
+                time.sleep(0.05)
+        assert s is not None
+        # frame: type, seq, a, b, len, aux  (32 bytes, little endian)
+        s.sendall(struct.pack("<IIQQII", 999, 1, 0, 0, 0, 0))
+        hdr = s.recv(32, socket.MSG_WAITALL)
+        typ, seq, _, _, ln, aux = struct.unpack("<IIQQII", hdr)
+        assert typ == 0x8000 and seq == 1 and aux == 1       # REPLY with the error flag
+        msg = s.recv(ln, socket.MSG_WAITALL)
+        assert b"unknown request" in msg
+        s.sendall(struct.pack("<IIQQII", 5, 2, 0, 0, 0xFFFFFFF0, 0))   # 4 GiB "payload"
+        assert s.recv(32) == b""                              # connection dropped
+        s.close()
+        assert procs[0].wait(timeout=20) == 0
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
