@@ -120,7 +120,7 @@ def build(with_cuda=True, verbose=False, force=False, tools=True, out_path=None)
                 lib.unlink()
             _run(["ar", "rcs", str(lib), *[str(o) for o in core_objs]], verbose)
     if tools and not with_cuda:
-        for name in ("cclo_emu", "emu_selftest", "emu_suite", "emu_bench"):
+        for name in ("cclo_emu", "emu_selftest", "emu_suite", "emu_bench", "emu_fuzz"):
             build_tool(name, verbose)
     if tools and with_cuda:
         lib_objs = [o for o, s in zip(objs, srcs) if s != BINDING and "bind_" not in s]
@@ -220,6 +220,7 @@ if __name__ == "__main__":
     ap.add_argument("--no-tools", action="store_true")
     ap.add_argument("--sanitize", choices=["address", "thread"], help="build build/bin/<tool>_<kind> only")
     ap.add_argument("--suite", action="store_true", help="with --sanitize: build the full emu_suite instead of emu_selftest")
+    ap.add_argument("--tool", default=None, help="with --sanitize: which csrc/tools/<tool>.cpp to build (emu_selftest, emu_suite, emu_fuzz)")
     ap.add_argument("--variant", metavar="NAME", help="with --define: build build/variants/NAME/accl_b200 with the extra macros")
     ap.add_argument("--define", action="append", default=[], metavar="MACRO")
     ap.add_argument("--check-define", action="append", default=[], metavar="MACRO",
@@ -232,6 +233,6 @@ if __name__ == "__main__":
         print(check_experimental(a.check_define))
         sys.exit(0)
     if a.sanitize:
-        print(build_sanitized(a.sanitize, a.verbose, "emu_suite" if a.suite else "emu_selftest"))
+        print(build_sanitized(a.sanitize, a.verbose, a.tool or ("emu_suite" if a.suite else "emu_selftest")))
         sys.exit(0)
     print(build(with_cuda=not a.cpu_only, verbose=a.verbose, force=a.force, tools=not a.no_tools))
