@@ -169,3 +169,13 @@ def test_engine_process_survives_garbage_on_the_control_port():
         for p in procs:
             if p.poll() is None:
                 p.kill()
+
+
+def test_cpp_fuzz_binary():
+    """csrc/tools/emu_fuzz.cpp: random call programs through the C++ API (the binary the TSan / ASan campaigns use)."""
+    from accl_b200.utils import build as b
+    exe = os.path.join(ROOT, "build", "bin", "emu_fuzz")
+    if not os.path.exists(exe):
+        b.build_tool("emu_fuzz")
+    r = subprocess.run([exe, "400", "5"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and " 0 failed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
