@@ -459,7 +459,20 @@ bool Engine::decode(EmuCall &c, Ctx &x, uint32_t &err) {
   }
   for (uint32_t r = 0; r < x.comm.size; ++r)
     x.comm.session[r] = exch_[exchmem::comm_rank_offset(d.comm, r, exchmem::CR_SESSION) / 4];
-  x.comm.sig = comm_signature(x.comm);
+  // Two communicators over the same members (e.g. a "sub"-communicator of everybody next to the global
+  // one) have separate sequence spaces, so their messages must not match each other's receives: mix in how
+  // many earlier table entries have the identical member list.  Every member creates the communicators of
+  // a given set collectively and in the same order, so all of them derive the same instance number.
+  uint32_t instance = 0;
+  for (uint32_t ci = 0; ci < d.comm; ++ci) {
+    if (exch_[exchmem::comm_offset(ci) / 4] != x.comm.size) continue;
+    bool same = true;
+    for (uint32_t r = 0; r < x.comm.size && same; ++r)
+      same = exch_[exchmem::comm_rank_offset(ci, r, exchmem::CR_SESSION) / 4] == x.comm.session[r];
+    instance += same ? 1u : 0u;
+  }
+  x.comm.sig = comm_signature(x.comm) ^ (instance * 0x9E3779B9u);
+  if (x.comm.sig == 0) x.comm.sig = 1;
   if (d.arithcfg >= exchmem::MAX_ARITHCFG) {
     err |= ARITH_ERROR;
     return false;

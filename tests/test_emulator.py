@@ -776,3 +776,27 @@ def test_bad_arguments_are_rejected():
             a.copy(s, d, 64)                          # count beyond the buffers
         a.barrier()
     A.run_ranks(2, fn, EAGER)
+
+
+def test_same_membership_communicators_do_not_cross_match():
+    """Two communicators over identical members have separate sequence spaces: a receive on one must not take a
+    message of the other even if that one arrived first with the same (source, tag, sequence number).  Found by
+    the sub-communicator property test (all ranks drawn into the 'sub'-communicator) under load."""
+    import time
+
+    def fn(a, r, w):
+        c2 = a.create_communicator(a.get_comm_group(0), r)
+        x, y = a.create_buffer(16), a.create_buffer(16)
+        if r == 0:
+            x.host[:] = 1.0
+            y.host[:] = 2.0
+            q1 = a.send(x, 16, 1, tag=5, comm_id=c2, run_async=True)
+            q2 = a.send(y, 16, 1, tag=5, run_async=True)
+            q1.wait()
+            q2.wait()
+        else:
+            time.sleep(0.2)                      # both messages sit in the rx pool
+            a.recv(y, 16, 0, tag=5)              # global communicator first, although its message arrived second
+            a.recv(x, 16, 0, tag=5, comm_id=c2)
+            assert torch.all(y.host == 2.0) and torch.all(x.host == 1.0)
+    A.run_ranks(2, fn, EAGER)
