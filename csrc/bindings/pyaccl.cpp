@@ -332,6 +332,12 @@ PYBIND11_MODULE(_C, m) {
     if (!rd) throw std::runtime_error("not a remote emulator backend");
     rd->shutdown_engine();
   }, gil_release());
+  m.def("emu_debug_state", [](ACCL &a) {
+    if (auto *rd = dynamic_cast<emu::RemoteDevice *>(a.device())) return rd->debug_state();
+    auto *d = dynamic_cast<emu::EmuDevice *>(a.device());
+    if (!d) throw std::runtime_error("not an emulator backend");
+    return d->engine().debug_state();
+  }, gil_release());
   m.def("emu_remote_debug_state", [](ACCL &a) {
     auto *rd = dynamic_cast<emu::RemoteDevice *>(a.device());
     if (!rd) throw std::runtime_error("not a remote emulator backend");

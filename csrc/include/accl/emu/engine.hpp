@@ -159,6 +159,8 @@ private:
 
   // ---- firmware: one handler per scenario; return error word or NOT_READY_ERROR
   uint32_t dispatch(EmuCall &c);
+  bool elder_conflict(const EmuCall &c);
+  void progress_parked_sends();
   uint32_t fw_config(EmuCall &c);
   uint32_t fw_copy(EmuCall &c);
   uint32_t fw_combine(EmuCall &c);
@@ -213,7 +215,7 @@ private:
   std::mutex q_m_;
   std::condition_variable q_cv_;
   std::deque<EmuCall> new_calls_, retry_calls_;
-  bool prefer_retry_ = false;
+  size_t older_parked_ = 0; // parked calls issued before the one being dispatched (control thread only)
   std::atomic<bool> stop_{false};
   std::thread control_, ingress_;
 

@@ -131,34 +131,51 @@ uint32_t Engine::timeout_us() {
 
 // --------------------------------------------------------------- control
 void Engine::control_loop() {
+  // Parked calls are kept in issue order and retried oldest first: two calls that wait for the same kind of
+  // event (e.g. several rendezvous sends to one peer with one tag, all waiting for an address note) must be
+  // served in the order they were issued — the non-overtaking rule of point-to-point messages.  A pass walks
+  // the list once; a fresh call is only admitted after a pass (or an empty list) and parks behind its elders.
   uint64_t seen_events = 0;
-  size_t fruitless = 0; // consecutive retries that made no progress
+  size_t cursor = 0;       // next parked call to try in this pass
+  bool progressed = false; // did this pass retire anything?
+  bool from_retry = false; // where the call being dispatched came from
   while (!stop_) {
     EmuCall c;
     bool have = false;
     {
       std::unique_lock<std::mutex> lk(q_m_);
-      if (new_calls_.empty() && (retry_calls_.empty() || fruitless >= retry_calls_.size())) {
-        // nothing runnable: sleep until a call, a mailbox event or a tick
-        q_cv_.wait_for(lk, std::chrono::milliseconds(retry_calls_.empty() ? 50 : 1), [&] {
-          return stop_.load() || !new_calls_.empty() || (!retry_calls_.empty() && mailbox_events_ != seen_events);
-        });
-        fruitless = 0;
+      if (cursor >= retry_calls_.size() && new_calls_.empty()) {
+        // a full pass over the parked calls and nothing new
+        if (!progressed || retry_calls_.empty()) {
+          // nothing runnable: sleep until a call, a mailbox event or a tick
+          q_cv_.wait_for(lk, std::chrono::milliseconds(retry_calls_.empty() ? 50 : 1), [&] {
+            return stop_.load() || !new_calls_.empty() || (!retry_calls_.empty() && mailbox_events_ != seen_events);
+          });
+        }
+        cursor = 0;
+        progressed = false;
       }
       if (stop_) break;
-      seen_events = mailbox_events_;
-      // round-robin between fresh calls and parked calls
-      const bool take_retry = !retry_calls_.empty() && (prefer_retry_ || new_calls_.empty());
-      if (take_retry) {
-        c = std::move(retry_calls_.front());
-        retry_calls_.pop_front();
+      if (mailbox_events_ != seen_events) {
+        // something arrived: the oldest parked call gets the first look at it
+        seen_events = mailbox_events_;
+        cursor = 0;
+      }
+      if (cursor < retry_calls_.size()) {
+        c = std::move(retry_calls_[cursor]);
+        retry_calls_.erase(retry_calls_.begin() + static_cast<std::ptrdiff_t>(cursor));
+        older_parked_ = cursor;
+        from_retry = true;
         have = true;
       } else if (!new_calls_.empty()) {
         c = std::move(new_calls_.front());
         new_calls_.pop_front();
+        older_parked_ = retry_calls_.size();
+        from_retry = false;
         have = true;
+        cursor = 0; // after a fresh call, start the next pass with the oldest parked call
+        progressed = false;
       }
-      prefer_retry_ = !prefer_retry_;
     }
     if (!have) continue;
     if (c.t0_ns == 0) {
@@ -179,12 +196,19 @@ void Engine::control_loop() {
         rc = RECEIVE_TIMEOUT_ERROR;
       } else {
         std::lock_guard<std::mutex> g(q_m_);
-        retry_calls_.push_back(std::move(c));
-        ++fruitless;
+        if (from_retry) {
+          // back to its place in the issue order; the pass moves on to the next one
+          const size_t at = std::min(older_parked_, retry_calls_.size());
+          retry_calls_.insert(retry_calls_.begin() + static_cast<std::ptrdiff_t>(at), std::move(c));
+          cursor = at + 1;
+        } else {
+          retry_calls_.push_back(std::move(c)); // the youngest
+        }
         continue;
       }
     }
-    fruitless = 0;
+    progressed = true;
+    if (from_retry) cursor = older_parked_; // the list closed up behind the retired call
     const uint64_t dur = now_ns() - c.t0_ns;
     write_exch(exchmem::RETCODE, rc);
     write_exch(exchmem::PERFCNT_LO, static_cast<uint32_t>(dur));
@@ -404,12 +428,62 @@ int Engine::rx_seek(uint32_t comm_sig, uint32_t src_global, uint32_t tag, uint32
   while (!stop_.load()) {
     if (scan()) break;
     if (!rx_overflow_.empty() && swap_in()) break;
-    if (rx_cv_.wait_until(lk, deadline) == std::cv_status::timeout) {
-      if (!scan() && !rx_overflow_.empty()) swap_in();
-      break;
-    }
+    // Wait in short slices.  Between slices let parked rendezvous sends go out: the peer we are waiting for may
+    // itself be waiting for one of them (A: isend(rendezvous) then eager recv / collective; B: recv, then the
+    // matching eager send) — this thread is the only one that can move them.
+    const auto now = std::chrono::steady_clock::now();
+    if (now >= deadline) break;
+    const auto slice = std::min<std::chrono::steady_clock::duration>(deadline - now, std::chrono::microseconds(200));
+    rx_cv_.wait_for(lk, slice);
+    lk.unlock();
+    progress_parked_sends();
+    lk.lock();
   }
   return found;
+}
+
+// Nested progress from inside a blocking eager wait (control thread only): try every parked point-to-point
+// send once, in issue order.  A rendezvous send never blocks (it returns NOT_READY while the receiver's address
+// note is missing), so this cannot recurse into another wait.
+void Engine::progress_parked_sends() {
+  size_t idx = 0;
+  for (;;) {
+    EmuCall c;
+    {
+      std::lock_guard<std::mutex> g(q_m_);
+      while (idx < retry_calls_.size() && static_cast<operation>(retry_calls_[idx].desc.scenario) != operation::send) ++idx;
+      if (idx >= retry_calls_.size()) return;
+      c = std::move(retry_calls_[idx]);
+      retry_calls_.erase(retry_calls_.begin() + static_cast<std::ptrdiff_t>(idx));
+    }
+    // the interrupted call's view of the data mover and of the queue must survive
+    const size_t saved_older = older_parked_;
+    uint64_t sa[3], sb[3];
+    std::memcpy(sa, prev_addr_, sizeof(sa));
+    std::memcpy(sb, prev_bytes_, sizeof(sb));
+    older_parked_ = idx;
+    uint32_t rc;
+    try {
+      rc = dispatch(c);
+    } catch (const std::exception &e) {
+      ACCL_ERROR_LOG("emulator rank " << rank_ << ": " << e.what());
+      rc = DMA_INTERNAL_ERROR;
+    }
+    older_parked_ = saved_older;
+    std::memcpy(prev_addr_, sa, sizeof(sa));
+    std::memcpy(prev_bytes_, sb, sizeof(sb));
+    if (rc == NOT_READY_ERROR) {
+      std::lock_guard<std::mutex> g(q_m_);
+      const size_t at = std::min(idx, retry_calls_.size());
+      retry_calls_.insert(retry_calls_.begin() + static_cast<std::ptrdiff_t>(at), std::move(c));
+      idx = at + 1;
+    } else {
+      const uint64_t dur = now_ns() - c.t0_ns;
+      if (c.req) c.req->complete(rc, dur);
+      if (c.on_done) c.on_done(rc);
+      // the list closed up: idx already points at the next candidate
+    }
+  }
 }
 
 void Engine::rx_release(int idx) {
@@ -662,6 +736,12 @@ std::string Engine::debug_state() {
   std::lock_guard<std::mutex> g(q_m_);
   o << "emulator rank " << rank_ << ": new=" << new_calls_.size() << " parked=" << retry_calls_.size()
     << " addr_notes=" << addr_notes_.size() << " done_notes=" << done_notes_.size();
+  for (const auto &c : retry_calls_)
+    o << "\n  parked: " << operation_name(static_cast<operation>(c.desc.scenario)) << " count=" << c.desc.count
+      << " peer/root=" << c.desc.root_src_dst << " tag=" << c.desc.tag << " step=" << c.step << " mask=0x" << std::hex << c.mask
+      << std::dec;
+  for (const auto &n : addr_notes_) o << "\n  addr note: from " << n.src << " tag=" << n.tag << " count=" << n.count;
+  for (const auto &n : done_notes_) o << "\n  done note: from " << n.src << " tag=" << n.tag << (n.barrier ? " (barrier token)" : "");
   return o.str();
 }
 

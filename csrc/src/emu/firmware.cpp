@@ -41,8 +41,41 @@ Operand next_of(const Operand &o) { // how the following segment addresses the s
 bool tag_match(uint32_t want, uint32_t have) { return want == TAG_ANY || have == TAG_ANY || want == have; }
 } // namespace
 
+// Ordering among calls in flight (the reference runs one call at a time; this engine keeps many): a call that
+// has not started yet must wait while an OLDER parked call competes for the same mailbox events —
+//  * point to point: an elder send to the same (communicator, destination) / recv from the same source:
+//    messages of one pair are matched in issue order (non-overtaking), whatever their tags;
+//  * collectives: any elder collective on the same communicator (their notes carry no per-call identity).
+// Without this a younger call dispatched at the wrong moment takes the address / completion note meant for its
+// elder (found by the point-to-point property test: three parked sends, same peer, same tag).
+bool Engine::elder_conflict(const EmuCall &c) {
+  const operation op = static_cast<operation>(c.desc.scenario);
+  const bool p2p = op == operation::send || op == operation::recv;
+  const bool coll = op == operation::bcast || op == operation::scatter || op == operation::gather || op == operation::allgather ||
+                    op == operation::reduce || op == operation::reduce_scatter || op == operation::allreduce ||
+                    op == operation::alltoall;
+  if (!p2p && !coll) return false;
+  std::lock_guard<std::mutex> g(q_m_);
+  const size_t n = std::min(older_parked_, retry_calls_.size());
+  for (size_t i = 0; i < n; ++i) {
+    const CallDesc &e = retry_calls_[i].desc;
+    if (e.comm != c.desc.comm) continue;
+    const operation eo = static_cast<operation>(e.scenario);
+    if (p2p) {
+      // regardless of tags: the other side may match with TAG_ANY, so a pair's messages stay in issue order
+      if (eo == op && e.root_src_dst == c.desc.root_src_dst) return true;
+    } else {
+      if (eo == operation::bcast || eo == operation::scatter || eo == operation::gather || eo == operation::allgather ||
+          eo == operation::reduce || eo == operation::reduce_scatter || eo == operation::allreduce || eo == operation::alltoall)
+        return true;
+    }
+  }
+  return false;
+}
+
 uint32_t Engine::dispatch(EmuCall &c) {
   const operation op = static_cast<operation>(c.desc.scenario);
+  if (c.step == 0 && c.mask == 0 && elder_conflict(c)) return NOT_READY_ERROR;
   switch (op) {
   case operation::config: return fw_config(c);
   case operation::nop: return 0;
@@ -844,11 +877,8 @@ uint32_t Engine::fw_allreduce(EmuCall &c) {
 uint32_t Engine::fw_barrier(EmuCall &c) {
   FW_DECODE(x);
   const uint32_t P = x.comm.size, me = x.comm.local_rank;
-  {
-    // calls parked before the barrier must drain first
-    std::lock_guard<std::mutex> g(q_m_);
-    if (!retry_calls_.empty() && c.step == 0 && c.mask == 0) return NOT_READY_ERROR;
-  }
+  // calls parked before the barrier must drain first (younger ones parked behind it do not hold it up)
+  if (older_parked_ != 0 && c.step == 0 && c.mask == 0) return NOT_READY_ERROR;
   if (P == 1) return 0;
   auto notify = [&](uint32_t to) {
     Packet p;

@@ -800,3 +800,34 @@ def test_same_membership_communicators_do_not_cross_match():
             a.recv(x, 16, 0, tag=5, comm_id=c2)
             assert torch.all(y.host == 2.0) and torch.all(x.host == 1.0)
     A.run_ranks(2, fn, EAGER)
+
+
+def test_parked_sends_keep_issue_order_and_do_not_starve_under_blocking_receives():
+    """Found by the point-to-point property test.  (1) Several rendezvous sends parked for the same peer and tag are
+    served in issue order (non-overtaking).  (2) A rank blocked in an eager receive still lets its parked rendezvous
+    sends go out: the peer needs them before it can send what the receive is waiting for."""
+    cfg = dict(n_egr_rx_bufs=8, egr_rx_buf_size=1024, max_egr_size=1024, max_rndzv_size=2048)
+
+    def fn(a, r, w):
+        big = [a.create_buffer(1232) for _ in range(3)]
+        small = a.create_buffer(64)
+        if r == 0:
+            for i, b in enumerate(big):
+                b.host[:] = float(i + 1)
+            reqs = [a.send(b, 1232, 1, tag=69, run_async=True) for b in big]   # three parked sends, same peer, same tag
+            a.recv(small, 64, 1, tag=7)          # eager receive: rank 1 only sends this after it has all three
+            assert torch.all(small.host == 9.0)
+            for q in reqs:
+                q.wait()
+                assert q.retcode() == 0
+        else:
+            import time
+            time.sleep(0.05)                     # rank 0 is already blocked in its receive
+            for i, b in enumerate(big):
+                a.recv(b, 1232, 0, tag=69)
+                assert torch.all(b.host == float(i + 1)), (i, b.host[:2])
+            small.host[:] = 9.0
+            a.send(small, 64, 0, tag=7)
+        a.barrier()
+    for _ in range(5):
+        A.run_ranks(2, fn, cfg)

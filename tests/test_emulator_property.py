@@ -235,3 +235,36 @@ def test_subcommunicators(world, data_, op, count, func, cfg, salt):
         a.allreduce(t, u, 8, SUM)
         assert torch.all(u.host == sum(range(w)))
     A.run_ranks(world, fn, cfg, timeout=120.0)
+
+
+@settings(max_examples=80, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(world=st.integers(2, 5), cfg=geometry(), salt=st.integers(0, 1000),
+       msgs=st.lists(st.tuples(st.integers(0, 4), st.integers(0, 4), st.integers(1, 2500), st.integers(0, 300), st.booleans()),
+                     min_size=1, max_size=12))
+def test_point_to_point_programs(world, cfg, salt, msgs):
+    """A random list of tagged messages between random pairs, sizes on both sides of the eager threshold.  Every
+    rank walks the list in order: asynchronous send if it is the source, blocking receive (exact tag or TAG_ANY) if
+    it is the destination — many messages outstanding per pair, eager and rendezvous interleaved."""
+    always_eager = cfg["max_egr_size"] >= (1 << 20)
+    if always_eager:
+        cfg = dict(cfg, egr_rx_buf_size=4096, n_egr_rx_bufs=32)
+    prog = [(s % world, d % world, min(n, 1000) if always_eager else n, tag, any_) for s, d, n, tag, any_ in msgs
+            if s % world != d % world]
+
+    def fn(a, r, w):
+        pending, keep = [], []
+        for i, (s, d, n, tag, any_) in enumerate(prog):
+            if r == s:
+                b = a.create_buffer(n)
+                b.host[:] = data(n, s, salt + i)
+                keep.append(b)
+                pending.append(a.send(b, n, d, tag=tag, run_async=True))
+            elif r == d:
+                b = a.create_buffer(n)
+                a.recv(b, n, s, tag=A.TAG_ANY if any_ else tag)
+                assert torch.equal(b.host, data(n, s, salt + i)), (i, s, d, n)
+        for q in pending:
+            q.wait()
+            assert q.retcode() == 0
+        a.barrier()
+    A.run_ranks(world, fn, cfg, timeout=120.0)
