@@ -107,6 +107,7 @@ def test_collectives_match_reference(world, steps, cfg):
         cfg = dict(cfg, egr_rx_buf_size=4096, n_egr_rx_bufs=32)
 
     def fn(a, r, w):
+        a.set_timeout(30_000_000)   # eager waits: peers may be seconds late on a loaded machine
         for op, count, root, func, salt in steps:
             run_op(a, r, w, op, min(count, 2000) if always_eager else count, root % w, func, salt)
     A.run_ranks(world, fn, cfg, timeout=120.0)
@@ -146,6 +147,7 @@ def test_dtypes_and_wire_compression(op, world, count, root, func, dtype, wire, 
     kw = dict(compress_dtype=wire) if wire is not None else {}
 
     def fn(a, r, w):
+        a.set_timeout(30_000_000)
         if op == "sendrecv":
             s, d = a.create_buffer(count, dtype), a.create_buffer(count, dtype)
             s.host[:] = vals(count, r)
@@ -195,6 +197,7 @@ def test_subcommunicators(world, data_, op, count, func, cfg, salt):
         count = min(count, 1000)
 
     def fn(a, r, w):
+        a.set_timeout(30_000_000)
         if r in members:
             ranks = [a.get_comm_group(0)[m] for m in members]
             me = members.index(r)
@@ -252,6 +255,7 @@ def test_point_to_point_programs(world, cfg, salt, msgs):
             if s % world != d % world]
 
     def fn(a, r, w):
+        a.set_timeout(30_000_000)
         pending, keep = [], []
         for i, (s, d, n, tag, any_) in enumerate(prog):
             if r == s:
