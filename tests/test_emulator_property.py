@@ -272,3 +272,45 @@ def test_point_to_point_programs(world, cfg, salt, msgs):
             assert q.retcode() == 0
         a.barrier()
     A.run_ranks(world, fn, cfg, timeout=120.0)
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(world=st.integers(2, 4), cfg=geometry(), salt=st.integers(0, 1000),
+       calls=st.lists(st.tuples(st.sampled_from(["allreduce", "bcast", "allgather"]), st.integers(1, 1500), st.integers(0, 3)),
+                      min_size=2, max_size=6))
+def test_async_collectives_in_flight(world, cfg, salt, calls):
+    """Several collectives issued back to back with run_async=True, waited for afterwards: the engine keeps them all
+    in flight; collectives on one communicator must still execute in issue order on every rank."""
+    always_eager = cfg["max_egr_size"] >= (1 << 20)
+    if always_eager:
+        cfg = dict(cfg, egr_rx_buf_size=4096, n_egr_rx_bufs=32)
+
+    def fn(a, r, w):
+        a.set_timeout(30_000_000)
+        issued = []
+        for i, (op, count, root) in enumerate(calls):
+            count = min(count, 1000) if always_eager else count
+            root %= w
+            if op == "allreduce":
+                s, d = a.create_buffer(count), a.create_buffer(count)
+                s.host[:] = data(count, r, salt + i)
+                req = a.allreduce(s, d, count, SUM, run_async=True)
+                exp = sum(data(count, q, salt + i) for q in range(w))
+            elif op == "bcast":
+                s = d = a.create_buffer(count)
+                s.host[:] = data(count, r, salt + i)
+                req = a.bcast(s, count, root, run_async=True)
+                exp = data(count, root, salt + i)
+            else:
+                s, d = a.create_buffer(count), a.create_buffer(count * w)
+                s.host[:] = data(count, r, salt + i)
+                req = a.allgather(s, d, count, run_async=True)
+                exp = torch.cat([data(count, q, salt + i) for q in range(w)])
+            issued.append((req, s, d, exp, i, op))
+        for req, s, d, exp, i, op in issued:
+            req.wait()
+            assert req.retcode() == 0, (i, op)
+            d.sync_from_device()
+            assert torch.equal(d.host, exp), (i, op)
+        a.barrier()
+    A.run_ranks(world, fn, cfg, timeout=120.0)
