@@ -232,8 +232,10 @@ private:
   std::deque<Packet> rx_overflow_;
 
   // rendezvous mailboxes (guarded by q_m_ so arrivals wake the control loop)
-  struct AddrNote { uint32_t comm_sig, src, tag, count; uint64_t vaddr; };
-  struct DoneNote { uint32_t comm_sig, src, tag; bool barrier; };
+  // kind: what posted the note (1 = point to point, 0x100 | opcode = that collective) — a send must never take
+  // the address a collective announced with TAG_ANY, and vice versa
+  struct AddrNote { uint32_t comm_sig, src, tag, count; uint64_t vaddr; uint32_t kind; };
+  struct DoneNote { uint32_t comm_sig, src, tag; bool barrier; uint32_t kind; };
   std::list<AddrNote> addr_notes_;
   std::list<DoneNote> done_notes_;
   uint64_t mailbox_events_ = 0;

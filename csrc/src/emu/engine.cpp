@@ -339,14 +339,14 @@ void Engine::ingress_loop() {
     }
     case MsgType::RNDZVS_INIT: {
       std::lock_guard<std::mutex> g(q_m_);
-      addr_notes_.push_back(AddrNote{p.hdr.comm_sig, p.hdr.src, p.hdr.tag, p.hdr.count, p.hdr.vaddr});
+      addr_notes_.push_back(AddrNote{p.hdr.comm_sig, p.hdr.src, p.hdr.tag, p.hdr.count, p.hdr.vaddr, p.hdr.seqn});
       ++mailbox_events_;
       q_cv_.notify_all();
       break;
     }
     case MsgType::RNDZVS_WR_DONE: {
       std::lock_guard<std::mutex> g(q_m_);
-      done_notes_.push_back(DoneNote{p.hdr.comm_sig, p.hdr.src, p.hdr.tag, p.hdr.strm != 0});
+      done_notes_.push_back(DoneNote{p.hdr.comm_sig, p.hdr.src, p.hdr.tag, p.hdr.strm != 0, p.hdr.seqn});
       ++mailbox_events_;
       q_cv_.notify_all();
       break;

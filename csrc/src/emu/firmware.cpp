@@ -75,7 +75,9 @@ bool Engine::elder_conflict(const EmuCall &c) {
 
 uint32_t Engine::dispatch(EmuCall &c) {
   const operation op = static_cast<operation>(c.desc.scenario);
-  if (c.step == 0 && c.mask == 0 && elder_conflict(c)) return NOT_READY_ERROR;
+  // collectives: checked here; point to point: only the rendezvous form waits for its elders (fw_send / fw_recv) —
+  // an eager send must never park, or younger eager traffic to the same peer would take its sequence number
+  if (op != operation::send && op != operation::recv && c.step == 0 && c.mask == 0 && elder_conflict(c)) return NOT_READY_ERROR;
   switch (op) {
   case operation::config: return fw_config(c);
   case operation::nop: return 0;
@@ -229,6 +231,11 @@ uint32_t Engine::egr_recv_reduce_send(Ctx &x, uint32_t src, Operand local, uint3
   return err;
 }
 
+// which kind of call a mailbox note belongs to (carried in the otherwise unused seqn field of note packets)
+template <typename C> static uint32_t note_kind(const C &x) {
+  return (x.op == operation::send || x.op == operation::recv) ? 1u : (0x100u | static_cast<uint32_t>(x.op));
+}
+
 void Engine::rndzv_post_addr(Ctx &x, uint32_t to_rank, uint64_t vaddr, uint32_t count, uint32_t tag) {
   Packet p;
   p.hdr.msg_type = static_cast<uint32_t>(MsgType::RNDZVS_INIT);
@@ -239,6 +246,7 @@ void Engine::rndzv_post_addr(Ctx &x, uint32_t to_rank, uint64_t vaddr, uint32_t 
   p.hdr.count = count;
   p.hdr.comm_sig = x.comm.sig;
   p.hdr.host = vaddr >= HOST_BASE;
+  p.hdr.seqn = note_kind(x);
   fabric_->send(std::move(p));
 }
 
@@ -246,7 +254,7 @@ bool Engine::rndzv_take_addr(Ctx &x, uint32_t from_rank, uint32_t tag, uint64_t 
   std::lock_guard<std::mutex> g(q_m_);
   const uint32_t src = x.comm.session[from_rank];
   for (auto it = addr_notes_.begin(); it != addr_notes_.end(); ++it)
-    if (it->comm_sig == x.comm.sig && it->src == src && tag_match(tag, it->tag)) {
+    if (it->comm_sig == x.comm.sig && it->src == src && it->kind == note_kind(x) && tag_match(tag, it->tag)) {
       vaddr = it->vaddr;
       addr_notes_.erase(it);
       return true;
@@ -257,7 +265,7 @@ bool Engine::rndzv_take_addr(Ctx &x, uint32_t from_rank, uint32_t tag, uint64_t 
 bool Engine::rndzv_take_any_addr(Ctx &x, uint32_t exclude_mask, uint32_t tag, uint32_t &from_rank, uint64_t &vaddr) {
   std::lock_guard<std::mutex> g(q_m_);
   for (auto it = addr_notes_.begin(); it != addr_notes_.end(); ++it) {
-    if (it->comm_sig != x.comm.sig || !tag_match(tag, it->tag)) continue;
+    if (it->comm_sig != x.comm.sig || it->kind != note_kind(x) || !tag_match(tag, it->tag)) continue;
     for (uint32_t r = 0; r < x.comm.size; ++r)
       if (x.comm.session[r] == it->src && !(exclude_mask & (1u << r))) {
         from_rank = r;
@@ -287,6 +295,7 @@ uint32_t Engine::rndzv_write(Ctx &x, uint32_t dst_rank, uint64_t src_addr, uint6
   p.hdr.dst = x.comm.session[dst_rank];
   p.hdr.tag = tag;
   p.hdr.comm_sig = x.comm.sig;
+  p.hdr.seqn = note_kind(x);
   fabric_->send(std::move(p));
   return err;
 }
@@ -295,7 +304,8 @@ bool Engine::rndzv_take_done(Ctx &x, uint32_t from_rank, uint32_t tag) {
   std::lock_guard<std::mutex> g(q_m_);
   const uint32_t src = x.comm.session[from_rank];
   for (auto it = done_notes_.begin(); it != done_notes_.end(); ++it)
-    if (it->comm_sig == x.comm.sig && it->src == src && it->barrier == (tag == BARRIER_TAG) && tag_match(tag, it->tag)) {
+    if (it->comm_sig == x.comm.sig && it->src == src && it->barrier == (tag == BARRIER_TAG) && it->kind == note_kind(x) &&
+        tag_match(tag, it->tag)) {
       done_notes_.erase(it);
       return true;
     }
@@ -305,7 +315,7 @@ bool Engine::rndzv_take_done(Ctx &x, uint32_t from_rank, uint32_t tag) {
 bool Engine::rndzv_take_any_done(Ctx &x, uint32_t exclude_mask, uint32_t tag, uint32_t &from_rank) {
   std::lock_guard<std::mutex> g(q_m_);
   for (auto it = done_notes_.begin(); it != done_notes_.end(); ++it) {
-    if (it->comm_sig != x.comm.sig || it->barrier != (tag == BARRIER_TAG) || !tag_match(tag, it->tag)) continue;
+    if (it->comm_sig != x.comm.sig || it->barrier != (tag == BARRIER_TAG) || it->kind != note_kind(x) || !tag_match(tag, it->tag)) continue;
     for (uint32_t r = 0; r < x.comm.size; ++r)
       if (x.comm.session[r] == it->src && !(exclude_mask & (1u << r))) {
         from_rank = r;
@@ -351,7 +361,9 @@ uint32_t Engine::fw_send(EmuCall &c) {
   FW_DECODE(x);
   if (x.root >= x.comm.size) return CONFIG_SWITCH_ERROR;
   if (!x.eager) {
-    // rendezvous: need the receiver's address first; park until it shows up
+    // rendezvous: elder rendezvous sends to the same peer go first (non-overtaking) ...
+    if (c.step == 0 && c.mask == 0 && elder_conflict(c)) return NOT_READY_ERROR;
+    // ... then we need the receiver's address; park until it shows up
     uint64_t vaddr = 0;
     if (!rndzv_take_addr(x, x.root, x.tag, vaddr)) return NOT_READY_ERROR;
     return rndzv_write(x, x.root, x.a0, vaddr, x.count, x.tag);
@@ -365,6 +377,7 @@ uint32_t Engine::fw_recv(EmuCall &c) {
   FW_DECODE(x);
   if (x.root >= x.comm.size) return CONFIG_SWITCH_ERROR;
   if (!x.eager) {
+    if (c.step == 0 && c.mask == 0 && elder_conflict(c)) return NOT_READY_ERROR; // elder receives from this source first
     Steps st(c.step);
     st([&] { rndzv_post_addr(x, x.root, x.a2, x.count * x.ubytes(), x.tag); return true; });
     if (!st([&] { return rndzv_take_done(x, x.root, x.tag); })) return NOT_READY_ERROR;
@@ -888,6 +901,7 @@ uint32_t Engine::fw_barrier(EmuCall &c) {
     p.hdr.tag = BARRIER_TAG;
     p.hdr.strm = 1; // marks a barrier token so data completions never match it
     p.hdr.comm_sig = x.comm.sig;
+    p.hdr.seqn = note_kind(x);
     fabric_->send(std::move(p));
   };
   Steps st(c.step);

@@ -831,3 +831,35 @@ def test_parked_sends_keep_issue_order_and_do_not_starve_under_blocking_receives
         a.barrier()
     for _ in range(5):
         A.run_ranks(2, fn, cfg)
+
+
+def test_notes_of_collectives_and_point_to_point_do_not_cross_match():
+    """A parked rendezvous send (tag t) and a rendezvous collective (TAG_ANY notes) wait for the same peer at the same
+    time: the collective must not take the address note of the peer's receive, nor the send the collective's.
+    Found by the mixed point-to-point / collective property test."""
+    cfg = dict(n_egr_rx_bufs=8, egr_rx_buf_size=256, max_egr_size=1024, max_rndzv_size=1 << 20)
+    n, m = 2460, 568
+
+    def fn(a, r, w):
+        a.set_timeout(30_000_000)
+        big, got = a.create_buffer(n), a.create_buffer(n)
+        s, d = a.create_buffer(m * w), a.create_buffer(m * w)
+        s.host[:] = torch.arange(m * w, dtype=torch.float32) + 1000 * r
+        req = None
+        if r == 0:
+            big.host[:] = 7.0
+            req = a.send(big, n, 1, tag=72, run_async=True)    # parks: rank 1 posts the receive late
+        if r == 1:
+            import time
+            time.sleep(0.05)
+            a.recv(got, n, 0, tag=72)
+            assert torch.all(got.host == 7.0)
+        a.alltoall(s, d, m)                                      # rendezvous, address notes carry TAG_ANY
+        for q in range(w):
+            assert torch.equal(d.host[q * m:(q + 1) * m], torch.arange(r * m, (r + 1) * m, dtype=torch.float32) + 1000 * q)
+        if req is not None:
+            req.wait()
+            assert req.retcode() == 0
+        a.barrier()
+    for _ in range(5):
+        A.run_ranks(3, fn, cfg)

@@ -314,3 +314,47 @@ def test_async_collectives_in_flight(world, cfg, salt, calls):
             assert torch.equal(d.host, exp), (i, op)
         a.barrier()
     A.run_ranks(world, fn, cfg, timeout=120.0)
+
+
+mixed_step = st.one_of(
+    st.tuples(st.just("coll"), st.sampled_from(OPS[1:] + ["barrier"]), st.integers(1, 1500), st.integers(0, 5),
+              st.sampled_from([SUM, MAX])),
+    st.tuples(st.just("msg"), st.integers(0, 4), st.integers(0, 4), st.integers(1, 2500), st.integers(0, 300)))
+
+
+@settings(max_examples=80, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(world=st.integers(2, 5), cfg=geometry(), salt=st.integers(0, 1000), steps=st.lists(mixed_step, min_size=2, max_size=8))
+def test_mixed_point_to_point_and_collectives(world, cfg, salt, steps):
+    """Asynchronous (possibly parked) sends interleaved with blocking collectives: a rank sitting in a collective must
+    still get its parked rendezvous sends out, or the peer that needs them never joins the collective."""
+    always_eager = cfg["max_egr_size"] >= (1 << 20)
+    if always_eager:
+        cfg = dict(cfg, egr_rx_buf_size=4096, n_egr_rx_bufs=32)
+
+    def fn(a, r, w):
+        a.set_timeout(30_000_000)
+        pending, keep = [], []
+        for i, st_ in enumerate(steps):
+            if st_[0] == "coll":
+                _, op, count, root, func = st_
+                run_op(a, r, w, op, min(count, 1000) if always_eager else count, root % w, func, salt + i)
+            else:
+                _, s, d, n, tag = st_
+                s, d = s % w, d % w
+                n = min(n, 1000) if always_eager else n
+                if s == d:
+                    continue
+                if r == s:
+                    b = a.create_buffer(n)
+                    b.host[:] = data(n, s, salt + i)
+                    keep.append(b)
+                    pending.append(a.send(b, n, d, tag=tag, run_async=True))
+                elif r == d:
+                    b = a.create_buffer(n)
+                    a.recv(b, n, s, tag=tag)
+                    assert torch.equal(b.host, data(n, s, salt + i)), i
+        for q in pending:
+            q.wait()
+            assert q.retcode() == 0
+        a.barrier()
+    A.run_ranks(world, fn, cfg, timeout=120.0)
