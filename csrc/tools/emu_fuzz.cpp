@@ -29,6 +29,8 @@ struct Step {
   unsigned count, root;
   reduceFunction func;
   unsigned salt;
+  bool msg = false;       // true: a point-to-point message src -> dst (asynchronous send, blocking receive)
+  unsigned src = 0, dst = 0, tag = 0;
 };
 
 // small integers: every sum is exact in fp32, results compare with ==
@@ -159,7 +161,15 @@ int main(int argc, char **argv) {
     unsigned egr = std::max(std::min(egrs[pick(0, 3)], buf * nb / 2), buf);
     const unsigned rv = std::max(rvs[pick(0, 3)], 2 * egr);
     std::vector<Step> steps(pick(1, 5));
-    for (auto &s : steps) s = Step{static_cast<Op>(pick(0, N_OPS - 1)), pick(1, 3000), pick(0, 5), pick(0, 1) ? reduceFunction::SUM : reduceFunction::MAX, pick(0, 1000)};
+    for (auto &s : steps) {
+      s = Step{static_cast<Op>(pick(0, N_OPS - 1)), pick(1, 3000), pick(0, 5), pick(0, 1) ? reduceFunction::SUM : reduceFunction::MAX, pick(0, 1000)};
+      if (pick(0, 9) < 3) { // mix in parked / eager point-to-point traffic between the collectives
+        s.msg = true;
+        s.src = pick(0, static_cast<unsigned>(W) - 1);
+        s.dst = pick(0, static_cast<unsigned>(W) - 1);
+        s.tag = pick(0, 300);
+      }
+    }
     auto devs = emu::make_inproc_world(W, 64u << 20);
     std::vector<std::unique_ptr<ACCL>> accls;
     for (auto &d : devs) accls.emplace_back(new ACCL(std::move(d)));
@@ -170,7 +180,36 @@ int main(int argc, char **argv) {
       ts.emplace_back([&, r] {
         try {
           accls[static_cast<size_t>(r)]->initialize(ranks, r, static_cast<int>(nb), buf, egr, rv);
-          for (const Step &s : steps) run_step(*accls[static_cast<size_t>(r)], r, W, s);
+          accls[static_cast<size_t>(r)]->free_request(accls[static_cast<size_t>(r)]->set_timeout(30000000)); // peers may be seconds late under a sanitizer
+          ACCL &a = *accls[static_cast<size_t>(r)];
+          std::vector<ACCLRequest *> pending;
+          std::vector<std::unique_ptr<Buffer<float>>> keep;
+          for (const Step &s : steps) {
+            if (!s.msg) {
+              run_step(a, r, W, s);
+              continue;
+            }
+            if (s.src == s.dst) continue;
+            if (static_cast<unsigned>(r) == s.src) {
+              auto b = a.create_buffer<float>(s.count, dataType::float32);
+              auto v = data(s.count, r, s.salt);
+              std::memcpy(b->buffer(), v.data(), v.size() * 4);
+              pending.push_back(a.send(*b, s.count, s.dst, s.tag, GLOBAL_COMM, false, dataType::none, true));
+              keep.push_back(std::move(b));
+            } else if (static_cast<unsigned>(r) == s.dst) {
+              auto b = a.create_buffer<float>(s.count, dataType::float32);
+              a.free_request(a.recv(*b, s.count, s.src, s.tag));
+              auto e = data(s.count, static_cast<int>(s.src), s.salt);
+              for (unsigned i = 0; i < s.count; ++i)
+                if ((*b)[i] != e[i]) throw std::runtime_error("message " + std::to_string(s.src) + "->" + std::to_string(s.dst) + ": data mismatch");
+            }
+          }
+          for (ACCLRequest *q : pending) {
+            a.wait(q);
+            if (a.get_retcode(q) != 0) throw std::runtime_error("asynchronous send failed");
+            a.free_request(q);
+          }
+          a.free_request(a.barrier());
         } catch (const std::exception &e) {
           errs[static_cast<size_t>(r)] = e.what();
         }
@@ -181,7 +220,10 @@ int main(int argc, char **argv) {
       if (!errs[static_cast<size_t>(r)].empty()) {
         if (!bad) {
           std::printf("FAIL program %d (seed %u): world %d, rx %u x %u, eager <= %u, rendezvous seg %u:", p, seed, W, nb, buf, egr, rv);
-          for (const Step &s : steps) std::printf(" %s(%u, root %u, %s)", op_name[s.op], s.count, s.root, s.func == reduceFunction::SUM ? "sum" : "max");
+          for (const Step &s : steps) {
+            if (s.msg) std::printf(" msg(%u->%u, %u, tag %u)", s.src, s.dst, s.count, s.tag);
+            else std::printf(" %s(%u, root %u, %s)", op_name[s.op], s.count, s.root, s.func == reduceFunction::SUM ? "sum" : "max");
+          }
           std::printf("\n");
         }
         std::printf("  rank %d: %s\n", r, errs[static_cast<size_t>(r)].c_str());
