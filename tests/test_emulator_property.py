@@ -358,3 +358,43 @@ def test_mixed_point_to_point_and_collectives(world, cfg, salt, steps):
             assert q.retcode() == 0
         a.barrier()
     A.run_ranks(world, fn, cfg, timeout=120.0)
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(cfg=geometry(), salt=st.integers(0, 1000),
+       ops=st.lists(st.tuples(st.sampled_from(["push", "pop", "through"]), st.integers(1, 2000)), min_size=1, max_size=10))
+def test_stream_port_is_a_fifo(cfg, salt, ops):
+    """The kernel stream port with loop-back behaves like one byte FIFO, whatever the chunking: copy_to_stream pushes,
+    copy_from_stream pops (possibly across push boundaries), copy_from_to_stream moves data from the head to the tail."""
+    from accl_b200 import DataType
+
+    def fn(a, r, w):
+        model = []          # expected FIFO content (floats)
+        k = 0
+        for op, n in ops:
+            if op == "push":
+                b = a.create_buffer(n)
+                b.host[:] = data(n, 0, salt + k)
+                k += 1
+                a.copy_to_stream(b, n)
+                model += b.host.tolist()
+            elif op == "pop":
+                n = min(n, len(model))
+                if n == 0:
+                    continue
+                b = a.create_buffer(n)
+                a.copy_from_stream(b, n)
+                assert b.host.tolist() == model[:n]
+                del model[:n]
+            else:
+                n = min(n, len(model))
+                if n == 0:
+                    continue
+                a.copy_from_to_stream(DataType.float32, n)
+                model += model[:n]
+                del model[:n]
+        if model:
+            b = a.create_buffer(len(model))
+            a.copy_from_stream(b, len(model))
+            assert b.host.tolist() == model
+    A.run_ranks(1, fn, cfg, timeout=60.0)
