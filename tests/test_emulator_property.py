@@ -398,3 +398,51 @@ def test_stream_port_is_a_fifo(cfg, salt, ops):
             a.copy_from_stream(b, len(model))
             assert b.host.tolist() == model
     A.run_ranks(1, fn, cfg, timeout=60.0)
+
+
+KINDS = ["device", "host_only", "p2p"]
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(op=st.sampled_from(["sendrecv", "allreduce", "bcast", "allgather", "reduce_scatter"]), world=st.integers(2, 4),
+       count=st.integers(1, 1500), ks=st.sampled_from(KINDS), kd=st.sampled_from(KINDS), cfg=geometry(), salt=st.integers(0, 100))
+def test_buffer_kinds(op, world, count, ks, kd, cfg, salt):
+    """Operands in device memory, host-only memory (the engine reaches across: OP*_HOST / RES_HOST flags) or
+    peer-visible memory, in every combination and on both protocols."""
+    if cfg["max_egr_size"] >= (1 << 20):
+        cfg = dict(cfg, egr_rx_buf_size=4096, n_egr_rx_bufs=32)
+        count = min(count, 1000)
+
+    def fn(a, r, w):
+        a.set_timeout(30_000_000)
+
+        def mk(n, kind):
+            return a.create_buffer(n, kind=getattr(A.BufferKind, kind))
+        if op == "sendrecv":
+            s, d = mk(count, ks), mk(count, kd)
+            s.host[:] = data(count, r, salt)
+            req = a.send(s, count, (r + 1) % w, tag=1, run_async=True)
+            a.recv(d, count, (r - 1) % w, tag=1)
+            req.wait()
+            assert torch.equal(d.host, data(count, (r - 1) % w, salt))
+        elif op == "allreduce":
+            s, d = mk(count, ks), mk(count, kd)
+            s.host[:] = data(count, r, salt)
+            a.allreduce(s, d, count, SUM)
+            assert torch.equal(d.host, sum(data(count, q, salt) for q in range(w)))
+        elif op == "bcast":
+            b = mk(count, ks)
+            b.host[:] = data(count, r, salt)
+            a.bcast(b, count, 1 % w)
+            assert torch.equal(b.host, data(count, 1 % w, salt))
+        elif op == "allgather":
+            s, d = mk(count, ks), mk(count * w, kd)
+            s.host[:] = data(count, r, salt)
+            a.allgather(s, d, count)
+            assert torch.equal(d.host, torch.cat([data(count, q, salt) for q in range(w)]))
+        else:
+            s, d = mk(count * w, ks), mk(count, kd)
+            s.host[:] = data(count * w, r, salt)
+            a.reduce_scatter(s, d, count, SUM)
+            assert torch.equal(d.host, sum(data(count * w, q, salt) for q in range(w))[r * count:(r + 1) * count])
+    A.run_ranks(world, fn, cfg, timeout=120.0)
