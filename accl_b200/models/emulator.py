@@ -20,25 +20,29 @@ import subprocess
 import sys
 
 
-def free_port_block(n):
-    """A base port with n consecutive free ports (best effort)."""
-    for _ in range(50):
+def free_port_block(n, also_at=()):
+    """A base port with n consecutive free ports (best effort); `also_at`: extra offsets whose n-port blocks must be
+    free as well (the engines' control ports live at base + 1000)."""
+    for _ in range(100):
         s = socket.socket()
         s.bind(("127.0.0.1", 0))
         base = s.getsockname()[1]
         s.close()
+        if base + max((0,) + tuple(also_at)) + n >= 65000:
+            continue
         ok = True
         socks = []
         try:
-            for i in range(n):
-                t = socket.socket()
-                t.bind(("127.0.0.1", base + i))
-                socks.append(t)
+            for off in (0,) + tuple(also_at):
+                for i in range(n):
+                    t = socket.socket()
+                    t.bind(("127.0.0.1", base + off + i))
+                    socks.append(t)
         except OSError:
             ok = False
         for t in socks:
             t.close()
-        if ok and base + n < 65000:
+        if ok:
             return base
     raise RuntimeError("no free port block found")
 
@@ -85,7 +89,7 @@ def spawn_engines(world, base_port=None, mem_mb=64, loopback=True, log_level=Non
     """Start one stand-alone engine process per rank (reference run.py: N x cclo_emu).  Rank r's engine
     listens for the other engines on base_port + r and for its driver on base_port + 1000 + r.
     Returns (procs, base_port); attach with `accl_b200.remote_rank(r, world, ctrl_port=base_port + 1000 + r)`."""
-    base_port = base_port or free_port_block(world)
+    base_port = base_port or free_port_block(world, also_at=(1000,))
     exe = engine_binary()
     procs = []
     for r in range(world):
