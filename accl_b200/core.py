@@ -335,6 +335,24 @@ class Accl:
         return getattr(self._a, name)
 
 
+def _raise_rank_errors(errors, hung, timeout):
+    """Report the most informative failure of a multi-rank run: a rank that timed out waiting for a peer is
+    usually a consequence, the peer's own error (assertion, bad argument...) the cause — show that one first and list
+    the others."""
+    failed = [(r, e) for r, e in enumerate(errors) if e is not None]
+    if failed:
+        def secondary(item):
+            return "TIMEOUT" in str(item[1][0]) or "NOT_READY" in str(item[1][0])
+        primary = next((f for f in failed if not secondary(f)), failed[0])
+        others = "".join(f"\n  also rank {r}: {type(e[0]).__name__}: {str(e[0]).splitlines()[0] if str(e[0]) else ''}"
+                         for r, e in failed if r != primary[0])
+        if hung:
+            others += f"\n  ranks {hung} still running after {timeout}s"
+        raise RuntimeError(f"rank {primary[0]} failed:\n{primary[1][1]}{others}") from primary[1][0]
+    if hung:
+        raise TimeoutError(f"ranks {hung} did not finish within {timeout}s")
+
+
 def emulator_world(world_size, mem_mb=256):
     """N un-initialised ranks of an in-process CPU emulator (drive each from its own thread)."""
     return [Accl(a, r, world_size) for r, a in enumerate(_C.make_emu_world(world_size, mem_mb))]
@@ -342,7 +360,7 @@ def emulator_world(world_size, mem_mb=256):
 
 def run_ranks(world_size, fn, init_kwargs=None, mem_mb=64, timeout=120.0):
     """Run fn(accl, rank, world) on every rank of a fresh emulator world, one
-    thread per rank; re-raises the first failure.  The harness used by the CPU
+    thread per rank; re-raises the most informative failure (a peer's own error before the time-outs it caused).  The harness used by the CPU
     test-suite (the reference uses mpirun + one emulator process per rank)."""
     accls = emulator_world(world_size, mem_mb)
     errors = [None] * world_size
@@ -362,11 +380,7 @@ def run_ranks(world_size, fn, init_kwargs=None, mem_mb=64, timeout=120.0):
     for t in threads:
         t.join(timeout)
     hung = [r for r, t in enumerate(threads) if t.is_alive()]
-    for r, e in enumerate(errors):
-        if e is not None:
-            raise RuntimeError(f"rank {r} failed:\n{e[1]}") from e[0]
-    if hung:
-        raise TimeoutError(f"ranks {hung} did not finish within {timeout}s")
+    _raise_rank_errors(errors, hung, timeout)
     for a in accls:
         a.deinit()
     return results
@@ -472,11 +486,7 @@ def run_cuda_ranks(devices, fn, init_kwargs=None, timeout=180.0, **cfg):
     for t in threads:
         t.join(timeout)
     hung = [r for r, t in enumerate(threads) if t.is_alive()]
-    for r, e in enumerate(errors):
-        if e is not None:
-            raise RuntimeError(f"rank {r} failed:\n{e[1]}") from e[0]
-    if hung:
-        raise TimeoutError(f"ranks {hung} did not finish within {timeout}s")
+    _raise_rank_errors(errors, hung, timeout)
     for a in accls:
         a.deinit()
     del accls
