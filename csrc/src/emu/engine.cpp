@@ -192,7 +192,7 @@ void Engine::control_loop() {
     if (rc == NOT_READY_ERROR) {
       // park it; give up after a generous deadline so a broken test fails instead of hanging
       const uint64_t waited_us = (now_ns() - c.t0_ns) / 1000;
-      if (waited_us > std::max<uint64_t>(60ull * 1000000ull, 60ull * timeout_us())) {
+      if (waited_us > std::max<uint64_t>(60ull * 1000000ull, 2ull * timeout_us())) {
         rc = RECEIVE_TIMEOUT_ERROR;
       } else {
         std::lock_guard<std::mutex> g(q_m_);
