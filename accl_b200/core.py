@@ -323,6 +323,18 @@ class Accl:
     def dump_exchange_memory(self):
         return self._a.dump_exchange_memory()
 
+    def set_tuning(self, name, value):
+        """CUDA backend: runtime knob (hybrid_16ths, nvls_unroll, nvls_ctas, reduce_push, bcast_flags, ll_max_bytes,
+        ll_oneshot_max, max_ctas, stream_loopback ...); must be set identically on every rank."""
+        _C.cuda_set_tuning(self._a, name, int(value))
+
+    def get_tuning(self, name):
+        return _C.cuda_get_tuning(self._a, name)
+
+    def drain(self):
+        """CUDA backend: wait until every call started so far has completed."""
+        _C.cuda_drain(self._a)
+
     def cuda_debug_state(self):
         """CUDA backend: sync-pad / eager counters of this rank's control block (and the per-call phase
         timing when built with ACCL_PHASE_TIMING).  Safe to call from another thread while a call hangs."""
@@ -416,11 +428,13 @@ def _prepare_cuda_env():
 
 
 def cuda_world(devices, heap_mb=256, multicast=True, max_ctas=8, engine=False, nvls_min_ranks=3, oneshot_kb=2048,
-               nvls_ops=-1):
+               nvls_ops=-1, **extra):
     """In-process world on real GPUs: rank i drives devices[i] (a device may
-    appear several times: ranks then share that GPU, without NVLS)."""
+    appear several times: ranks then share that GPU, without NVLS).  `extra`: engine_workers, engine_idle_us,
+    stage_kb, ll_kb and every `set_tuning` knob."""
     _prepare_cuda_env()
-    impls = _C.make_cuda_world(list(devices), heap_mb, multicast, max_ctas, engine, nvls_min_ranks, oneshot_kb, nvls_ops)
+    impls = _C.make_cuda_world(list(devices), heap_mb, multicast, max_ctas, engine, nvls_min_ranks, oneshot_kb, nvls_ops,
+                               {k: int(v) for k, v in extra.items()})
     return [Accl(a, r, len(devices), cuda_device=devices[r]) for r, a in enumerate(impls)]
 
 
@@ -443,7 +457,7 @@ def bind_to_gpu_numa_node(device):
 
 
 def cuda_rank(rank=None, world_size=None, device=None, addr=None, port=None, heap_mb=1024, multicast=True,
-              max_ctas=32, engine=False, nvls_min_ranks=3, oneshot_kb=2048, nvls_ops=-1):
+              max_ctas=32, engine=False, nvls_min_ranks=3, oneshot_kb=2048, nvls_ops=-1, **extra):
     """One rank per process (torchrun): RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT."""
     _prepare_cuda_env()
     rank = int(os.environ.get("RANK", 0)) if rank is None else rank
@@ -457,7 +471,7 @@ def cuda_rank(rank=None, world_size=None, device=None, addr=None, port=None, hea
     if os.environ.get("ACCL_BIND_NUMA", "1") != "0":
         bind_to_gpu_numa_node(device)
     impl = _C.make_cuda_rank(rank, world_size, device, addr, port, heap_mb, multicast, max_ctas, engine,
-                             nvls_min_ranks, oneshot_kb, nvls_ops)
+                             nvls_min_ranks, oneshot_kb, nvls_ops, {k: int(v) for k, v in extra.items()})
     return Accl(impl, rank, world_size, cuda_device=device)
 
 

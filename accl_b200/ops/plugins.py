@@ -4,8 +4,11 @@
   K-slice on the tcgen05 tensor cores and each finished tile is added straight
   into the owner rank's output shard over NVLink (no intermediate C, no
   separate reduce_scatter kernel).
-* vadd_allreduce: the vector-add plugin; the kernel computes x + y and then
-  issues the all-reduce itself through the device API (persistent engine).
+* vadd_allreduce: the vector-add plugin; the kernel computes x + y chunk by
+  chunk and hands every finished chunk to the persistent engine itself
+  (device API, all_reduce_async) while it computes the next one.
+* vadd_put / stream_pull: the reference's vadd_put example — x + 1 pushed into
+  a stream of the destination rank while computing; the consumer drains it.
 """
 import torch
 
@@ -36,15 +39,33 @@ def gemm_reduce_scatter(accl: Accl, a: torch.Tensor, w: torch.Tensor, out: Buffe
     return out
 
 
-def vadd_allreduce(accl: Accl, x: Buffer, y: Buffer, out: Buffer, tmp: Buffer = None, count: int = None):
-    """out = allreduce_sum(x + y) (fp32).  Returns a 1-element int32 CUDA tensor that receives the
-    engine's status word (0 = success) once the kernel has finished."""
+def vadd_allreduce(accl: Accl, x: Buffer, y: Buffer, out: Buffer, tmp: Buffer = None, count: int = None,
+                   chunk_elems: int = 0):
+    """out = allreduce_sum(x + y) (fp32), produced and reduced in chunks of `chunk_elems` (0: 1 Mi elements).
+    Returns a 1-element int32 CUDA tensor that receives the engine's status word (0 = success) once the kernel
+    has finished."""
     count = x.length if count is None else count
     if tmp is None:
         tmp = accl.create_buffer(count, torch.float32)
     status = torch.full((1,), -1, dtype=torch.int32, device=torch.device("cuda", accl.cuda_device))
-    _C.vadd_allreduce(accl.impl, x.impl, y.impl, tmp.impl, out.impl, count, status.data_ptr(), _stream_handle(accl))
+    _C.vadd_allreduce(accl.impl, x.impl, y.impl, tmp.impl, out.impl, count, status.data_ptr(), _stream_handle(accl),
+                      chunk_elems)
     status._keep = tmp
+    return status
+
+
+def vadd_put(accl: Accl, src: Buffer, count: int, dst_rank: int, stream_id: int = 9):
+    """The reference's vadd_put user kernel: src + 1 (fp32) is pushed tile by tile into stream `stream_id` of rank
+    `dst_rank` while it is being computed (device::Data::push).  Returns the status tensor."""
+    status = torch.full((1,), -1, dtype=torch.int32, device=torch.device("cuda", accl.cuda_device))
+    _C.vadd_put(accl.impl, src.impl, count, dst_rank, stream_id, status.data_ptr(), _stream_handle(accl))
+    return status
+
+
+def stream_pull(accl: Accl, dst: Buffer, count: int, stream_id: int = 9):
+    """Drain `count` fp32 of stream `stream_id` of this rank into `dst` (device::Data::pull).  Returns the status tensor."""
+    status = torch.full((1,), -1, dtype=torch.int32, device=torch.device("cuda", accl.cuda_device))
+    _C.stream_pull(accl.impl, dst.impl, count, stream_id, status.data_ptr(), _stream_handle(accl))
     return status
 
 

@@ -32,13 +32,39 @@ using namespace accl;
 
 namespace {
 
+// Handle of one started call.  Dropping the Python object releases the request in the engine's registry (a
+// training loop issuing asynchronous calls and never calling free() must not grow it without bound).
 struct PyRequest {
   ACCL *owner = nullptr;
   ACCLRequest *h = nullptr;
-  bool valid() const { return owner && h; }
+  std::shared_ptr<std::atomic<bool>> alive;
+  PyRequest() = default;
+  PyRequest(ACCL *o, ACCLRequest *r) : owner(o), h(r), alive(o ? o->alive_token() : nullptr) {}
+  PyRequest(PyRequest &&o) noexcept : owner(o.owner), h(o.h), alive(std::move(o.alive)) { o.h = nullptr; }
+  PyRequest &operator=(PyRequest &&o) noexcept {
+    release();
+    owner = o.owner;
+    h = o.h;
+    alive = std::move(o.alive);
+    o.h = nullptr;
+    return *this;
+  }
+  PyRequest(const PyRequest &) = delete;
+  PyRequest &operator=(const PyRequest &) = delete;
+  ~PyRequest() { release(); }
+  void release() {
+    if (owner && h && alive && alive->load()) {
+      try {
+        owner->free_request(h);
+      } catch (...) {
+      }
+    }
+    h = nullptr;
+  }
+  bool valid() const { return owner && h && alive && alive->load(); }
 };
 
-PyRequest wrap(ACCL &a, ACCLRequest *h) { return PyRequest{&a, h}; }
+PyRequest wrap(ACCL &a, ACCLRequest *h) { return PyRequest(&a, h); }
 
 using gil_release = py::call_guard<py::gil_scoped_release>;
 
@@ -96,7 +122,7 @@ PYBIND11_MODULE(_C, m) {
       .def("test", [](PyRequest &r) { return r.valid() ? r.owner->test(r.h) : true; })
       .def("duration_ns", [](PyRequest &r) { return r.valid() ? r.owner->get_duration(r.h) : 0; })
       .def("retcode", [](PyRequest &r) { return r.valid() ? r.owner->get_retcode(r.h) : 0u; })
-      .def("free", [](PyRequest &r) { if (r.valid()) r.owner->free_request(r.h); r.h = nullptr; })
+      .def("free", [](PyRequest &r) { r.release(); })
       .def_property_readonly("valid", &PyRequest::valid);
 
   py::class_<BaseBuffer>(m, "Buffer")

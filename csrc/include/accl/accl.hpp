@@ -7,6 +7,7 @@
 // written against it ports by changing the constructor.  "fpga" in argument
 // names means "device" (a B200 here).
 #pragma once
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <memory>
@@ -28,6 +29,9 @@ public:
   ~ACCL();
   ACCL(const ACCL &) = delete;
   ACCL &operator=(const ACCL &) = delete;
+  // true while this object is alive: lets request handles held elsewhere (language bindings) release themselves
+  // in their destructors without touching a destroyed engine
+  std::shared_ptr<std::atomic<bool>> alive_token() const { return alive_; }
 
   // Configure the engine: eager RX buffers, rendezvous scratch, global
   // communicator, arithmetic table, tuning registers, thresholds; then enable
@@ -212,6 +216,7 @@ private:
   bool config_rdy = false;
   void *stream_ = nullptr;
   int trace_rank_ = 0; // pid of this instance's events in ACCL_TRACE output
+  std::shared_ptr<std::atomic<bool>> alive_ = std::make_shared<std::atomic<bool>>(true);
 };
 
 } // namespace accl

@@ -12,6 +12,7 @@
 
 #include <memory>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "accl/allocator.hpp"
@@ -30,7 +31,7 @@ class module_;
 namespace accl {
 namespace cuda {
 
-constexpr size_t STREAM_FIFO_BYTES = 4u << 20; // device-side stream port capacity per rank (power of two)
+constexpr size_t STREAM_FIFO_BYTES = 1u << 20; // capacity of one device-side stream FIFO (power of two; scaled down on small heaps)
 
 struct CudaConfig {
   int device = 0;
@@ -42,7 +43,14 @@ struct CudaConfig {
   size_t oneshot_max_bytes = 2048 << 10; // allreduce: pull-everything one-shot while bytes x ranks <= this
   uint32_t nvls_ops = NVLS_OPS_DEFAULT;  // which operations may use multimem (bit = operation code)
   bool engine = false;         // route calls through the persistent engine kernel
-  int engine_idle_us = 200;    // engine kernel parks itself after this idle time (0 = never)
+  int engine_idle_us = 1000;   // engine kernel parks itself after this idle time (0 = never)
+  int engine_workers = 0;      // worker CTAs of the engine (0: max_ctas, never more than SMs - 16)
+  int nvls_ctas = 64;          // channel cap of the NVLS two-shot all-reduce
+  size_t stage_bytes = 0;      // staging region per (bank, parity, source) of ALGO_STAGED (0: sized from the heap)
+  size_t ll_bytes = 0;         // same for ALGO_LL
+  size_t ll_max_bytes = 16u << 10;   // per-peer message size up to which the flag-in-data protocol is used
+  size_t ll_oneshot_max = 32u << 10; // all-reduce: one hop (everybody sends everything) up to this size
+  Tune tune{0, 8, 0, 0, 0, {0, 0, 0}};
 };
 
 class CudaDevice;
@@ -54,6 +62,7 @@ struct CudaRequest : public BaseRequest {
   cudaStream_t stream = nullptr; // stream the call was enqueued on (fallback for long waits)
   uint32_t slot = 0, seq = 0;
   bool immediate = false; // completed on the host (config calls)
+  bool unordered = false; // engine call whose proxy does not hold the stream: completion is only visible in the record
   std::vector<std::shared_ptr<BufferStorage>> temps; // staging buffers that live as long as the call
   std::vector<std::pair<BaseBuffer *, std::shared_ptr<BufferStorage>>> copy_out;
   void wait() override;
@@ -99,16 +108,27 @@ public:
   RangeAllocator &allocator() { return *alloc_; }
   HostCompletion *host_completions() { return hc_host_; }
   struct PlanCfg plan_cfg() const;
+  // runtime tuning knobs ("hybrid_16ths", "nvls_unroll", "reduce_push", "bcast_flags", "nvls_ctas", "ll_max_bytes",
+  // "ll_oneshot_max", "max_ctas"); must be set identically on every rank.  Returns false for an unknown name.
+  bool set_tuning(const std::string &name, long value);
+  long get_tuning(const std::string &name) const;
+  // wait until every call started so far has completed (engine quiesce before direct launches share its channels)
+  void drain();
   bool build_work_item(const Options &o, const CallDesc &d, WorkItem &w, uint32_t &err);
   uint32_t timeout_us() const;
   Oob &oob() { return *oob_; }
   class Engine *engine() { return engine_.get(); }
-  unsigned int *plugin_counter(); // zero-initialised device word for plugin kernels
+  void *plugin_scratch(size_t bytes); // zero-initialised device memory for plugin kernels (grown on demand)
+  // FIFO a stream id is served by: the id itself, or 0 while every id loops back through one FIFO (default)
+  uint32_t stream_port_id(uint32_t id) const { return strm_loopback_ ? 0u : id; }
 
 private:
   uint32_t host_config(const CallDesc &d);
   void setup_eager_area();
   void sync_ctrl_word(uint32_t byte_off);
+  void apply_env_tuning();
+  void drain_locked();
+  bool strm_loopback_ = true; // every stream id is served by FIFO 0 (the reference's loopback user kernel)
 
   std::shared_ptr<Oob> oob_;
   CudaConfig cfg_;
@@ -127,13 +147,13 @@ private:
   RequestRegistry requests_;
   std::shared_ptr<BufferStorage> egr_area_;
   std::shared_ptr<BufferStorage> strm_area_;
-#ifdef ACCL_EXPERIMENTAL_REDUCE_PUSH
-  std::shared_ptr<BufferStorage> scr_area_; // scratch of the write-only rooted reduce (docs/roadmap.md #1)
-#endif
+  std::shared_ptr<BufferStorage> stg_area_, ll_area_; // staging of the one-way protocols (staged.cuh)
+  std::shared_ptr<BufferStorage> scr_area_;           // scratch of the write-only rooted reduce
   friend struct CudaRequest;
   friend class Engine;
   std::unique_ptr<class Engine> engine_;
-  unsigned int *plugin_counter_ = nullptr;
+  void *plugin_scratch_ = nullptr;
+  size_t plugin_scratch_bytes_ = 0;
 };
 
 // In-process world: N ranks as threads of this process, rank i on devices[i]

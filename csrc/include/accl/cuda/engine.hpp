@@ -15,9 +15,11 @@ class Engine {
 public:
   explicit Engine(CudaDevice &dev);
   ~Engine();
-  // enqueue one planned work item; completion is published to `hc` and the
-  // user stream `s` is made to wait for it (stream-ordered like a kernel)
-  void submit(const WorkItem &w, HostCompletion *hc, cudaStream_t s);
+  // enqueue one planned work item through a proxy kernel on stream `s` (ordered after the work already
+  // queued there); completion is published to `hc`; with `stream_waits` the proxy also holds the stream until
+  // the engine has retired the call (stream-ordered like a direct launch)
+  void submit(const WorkItem &w, HostCompletion *hc, cudaStream_t s, bool stream_waits);
+  int workers() const;
   // park the engine kernel now (blocks until it has left the GPU)
   void stop();
   // device-side clients (plugin kernels) are about to issue commands: keep the engine resident

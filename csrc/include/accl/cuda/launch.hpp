@@ -28,9 +28,10 @@ void preload_vadd_kernels();
 
 // Device-side stream port (the user-kernel <-> engine AXI streams of the reference): a byte
 // FIFO in the heap.  pop: FIFO -> dst (local heap offset); push: src -> FIFO of rank `dst_rank`.
-cudaError_t launch_stream_pop(const DevWorld &w, uint64_t dst_off, uint64_t bytes, uint32_t timeout_us, cudaStream_t stream);
-cudaError_t launch_stream_push(const DevWorld &w, uint32_t dst_rank, uint64_t src_off, uint64_t bytes, uint32_t timeout_us,
-                               cudaStream_t stream);
+cudaError_t launch_stream_pop(const DevWorld &w, uint64_t dst_off, uint64_t bytes, uint32_t stream_id, uint32_t timeout_us,
+                              cudaStream_t stream);
+cudaError_t launch_stream_push(const DevWorld &w, uint32_t dst_rank, uint64_t src_off, uint64_t bytes, uint32_t stream_id,
+                               uint32_t timeout_us, cudaStream_t stream);
 
 // zero the protocol state of my control block (soft reset)
 cudaError_t launch_reset_ctrl(const DevWorld &w, cudaStream_t stream);

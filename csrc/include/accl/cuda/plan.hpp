@@ -26,7 +26,12 @@ struct PlanCfg {
   // bcast and reduce.  Measured on 4 x B200 (profiles/sweep_4gpu_*.csv): allgather and
   // reduce_scatter move less data per link with peer stores / loads than through the switch.
   uint32_t nvls_ops;
-  uint32_t pad;
+  uint32_t nvls_ctas;      // channel cap of the NVLS two-shot all-reduce (fewer, fatter CTAs win through the switch)
+  uint32_t stg_bytes;      // staging region per (bank, parity, source) of ALGO_STAGED; 0: protocol off
+  uint32_t ll_bytes;       // same for ALGO_LL
+  uint32_t ll_max_bytes;   // per-peer message size up to which the flag-in-data protocol is used
+  uint32_t ll_oneshot_max; // all-reduce: everybody-sends-everything (one hop) up to this size, two hops above
+  Tune tune;
 };
 constexpr uint32_t NVLS_OPS_DEFAULT = (1u << static_cast<uint32_t>(operation::allreduce)) |
                                       (1u << static_cast<uint32_t>(operation::bcast)) |
@@ -39,12 +44,35 @@ ACCL_HD uint32_t plan_ctas(uint64_t bytes, uint64_t per_cta, uint32_t cap) {
   return static_cast<uint32_t>(n);
 }
 
+// One-way staged protocols (staged.cuh): does a per-peer message of `m` bytes fit, and on how many channels?
+// Every channel owns a fixed 1 / STG_CH slice of the staging region.  Returns 0 when it does not fit.
+ACCL_HD uint32_t plan_staged_ctas(uint64_t m, bool ll, const PlanCfg &cfg, uint32_t cap) {
+  const uint64_t region = ll ? cfg.ll_bytes : cfg.stg_bytes;
+  const uint64_t slice = (region / static_cast<uint64_t>(STG_CH)) & ~127ull;
+  if (!slice) return 0;
+  const uint64_t unit = ll ? 8 : 16;                       // payload granule of a part (staged.cuh stg_part)
+  const uint64_t units = (m + unit - 1) / unit;
+  const uint64_t per_slice = slice / 16;                   // LL: 8 payload bytes per 16-byte line; plain: 16 per 16
+  uint64_t need = (units + per_slice - 1) / per_slice;     // channels needed for capacity
+  uint64_t want = ll ? (units + 511) / 512 : (m + (32u << 10) - 1) / (32u << 10); // channels wanted for parallelism
+  const uint64_t lim = cap < static_cast<uint32_t>(STG_CH) ? cap : static_cast<uint32_t>(STG_CH);
+  if (need < 1) need = 1;
+  if (need > lim) return 0;
+  if (want < need) want = need;
+  if (want > lim) want = lim;
+  // parts are ceil(units / n): re-check capacity for the chosen n
+  while (want < lim && (units + want - 1) / want > per_slice) ++want;
+  if ((units + want - 1) / want > per_slice) return 0;
+  return static_cast<uint32_t>(want);
+}
+
 ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
   const operation op = static_cast<operation>(w.desc.scenario);
   const uint64_t ubytes = static_cast<uint64_t>(w.desc.count) * dtype_bytes(static_cast<dataType>(w.udtype));
   const uint32_t P = w.comm_size;
   const uint32_t cap = cfg.max_ctas < static_cast<uint32_t>(MAX_CH) ? cfg.max_ctas : static_cast<uint32_t>(MAX_CH);
   w.flags = cfg.has_mc ? WF_USE_MC : 0;
+  w.tune = cfg.tune;
   if (op == operation::nop || op == operation::config) {
     w.algo = ALGO_LOCAL;
     w.n_ctas = 1;
@@ -65,11 +93,38 @@ ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
       op == operation::scatter || op == operation::gather)
     moved = ubytes * P;
   const bool compressed = w.desc.compression_flags != 0;
+  const bool p2p = op == operation::send || op == operation::recv;
   const bool eager = compressed || ubytes <= exch[exchmem::MAX_EAGER_SIZE / 4];
+  if (eager && !compressed && !p2p && ubytes && cfg.ll_bytes) {
+    // one-way staged exchange: flag-in-data (LL) while latency dominates, payload + release flag above
+    uint64_t m = ubytes;
+    uint32_t extra = 0;
+    bool ok = true;
+    if (op == operation::allreduce) {
+      if (ubytes <= cfg.ll_oneshot_max || ubytes % (16ull * P) != 0) extra = WF_ONESHOT; // everybody receives everything
+      else m = ubytes / P;                                                               // shards: reduce-scatter + all-gather
+      // a one-shot of a large odd-sized message would move P x the bytes: leave it to the slot path
+      if ((extra & WF_ONESHOT) && ubytes > 4ull * cfg.ll_oneshot_max && ubytes > (256u << 10)) ok = false;
+    }
+    if (ok) {
+      uint32_t n = m <= cfg.ll_max_bytes ? plan_staged_ctas(m, true, cfg, cap) : 0;
+      if (n) {
+        w.algo = ALGO_LL;
+      } else {
+        n = plan_staged_ctas(m, false, cfg, cap);
+        if (n) w.algo = ALGO_STAGED;
+      }
+      if (n) {
+        w.flags |= extra;
+        w.n_ctas = n;
+        return;
+      }
+    }
+  }
   if (eager) {
     w.algo = ALGO_EAGER;
     const uint32_t ecap = cap < static_cast<uint32_t>(EGR_CH) ? cap : static_cast<uint32_t>(EGR_CH);
-    w.n_ctas = (op == operation::send || op == operation::recv) ? 1 : plan_ctas(ubytes, 16u << 10, ecap);
+    w.n_ctas = p2p ? 1 : plan_ctas(ubytes, 16u << 10, ecap);
     return;
   }
   const bool nvls = cfg.has_mc && P >= cfg.nvls_min_ranks && P == cfg.heap_world &&
@@ -77,13 +132,21 @@ ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
   w.algo = nvls ? ALGO_NVLS : ALGO_P2P;
   // one-shot (everybody pulls everything) moves P x the bytes of two-shot: only while latency dominates
   if (op == operation::allreduce && ubytes * P <= cfg.oneshot_max_bytes) w.algo = ALGO_P2P_ONESHOT;
-  if (op == operation::send || op == operation::recv) w.algo = ALGO_P2P;
+  if (p2p) w.algo = ALGO_P2P;
   uint32_t c = cap;
-  // measured on 8 x B200 (profiles/sweep_8gpu_{nvls,p2p}*.csv, 64 vs 128 CTAs): two-shot all-reduce is
-  // 5-25 % faster with 64 channels through the switch at every size and up to 128 MiB over peer loads /
-  // stores (fewer flag round trips per byte); the other collectives do not care
-  if (op == operation::allreduce && (w.algo == ALGO_NVLS || ubytes <= (128ull << 20)) && c > 64) c = 64;
+  // measured on 8 x B200 (profiles/sweep_8gpu_{nvls,p2p}*.csv, 64 vs 128 CTAs): two-shot all-reduce through the
+  // switch is 5-25 % faster with 64 channels at every size (fewer flag round trips per byte); peer loads / stores
+  // want every channel they can get (2 x B200: 64 MiB in 189 us with 64 CTAs, 120 us with 128)
+  if (op == operation::allreduce && w.algo == ALGO_NVLS && cfg.nvls_ctas && c > cfg.nvls_ctas) c = cfg.nvls_ctas;
   w.n_ctas = plan_ctas(moved, 128u << 10, c);
+}
+
+// signature of a communicator's member list (identical on all members): names its protocol-state bank
+ACCL_HD uint32_t comm_signature(const uint8_t *members, uint32_t n) {
+  uint32_t h = 2166136261u ^ n;
+  for (uint32_t i = 0; i < n; ++i) h = (h ^ members[i]) * 16777619u;
+  h ^= h >> 15;
+  return h & 0xFFFFFFu;
 }
 
 // Decode + plan.  Returns an error word (0 = ok).
@@ -114,6 +177,9 @@ ACCL_HD uint32_t build_work_item_hd(const uint32_t *exch, const PlanCfg &cfg, ui
   w.ratio_log = exch[ab + exchmem::AC_RATIO_LOG];
   w.arith_compressed = exch[ab + exchmem::AC_ARITH_COMPRESSED];
   w.timeout_us = timeout_us;
+  w.comm_sig = comm_signature(w.members, w.comm_size);
+  w.bank = w.comm_sig % static_cast<uint32_t>(N_BANKS);
+  w.hc_ptr = 0;
   const operation op = static_cast<operation>(d.scenario);
   const bool rooted = op == operation::send || op == operation::recv || op == operation::bcast ||
                       op == operation::scatter || op == operation::gather || op == operation::reduce;

@@ -29,11 +29,19 @@ struct GemmRsArgs {
 // and no separate collective.  Returns after enqueueing.
 cudaError_t launch_gemm_rs(CudaDevice &dev, const GemmRsArgs &args, cudaStream_t stream);
 
-// vector add whose result feeds an all-reduce issued by the kernel itself
-// through the device API (engine must be enabled): out = allreduce_sum(x + y)
+// vector add whose result feeds an all-reduce issued by the kernel itself through the device API (engine must be
+// enabled): out = allreduce_sum(x + y).  The vector is produced in chunks of `chunk_elems` (0: 1 Mi elements); each
+// finished chunk is handed to the engine at once (all_reduce_async) while the kernel computes the next one.
 cudaError_t launch_vadd_allreduce(CudaDevice &dev, uint64_t x_off, uint64_t y_off, uint64_t tmp_off, uint64_t out_off,
-                                  uint32_t count, uint32_t comm_adr, uint32_t dpcfg_adr, uint32_t *status_dev,
+                                  uint32_t count, uint32_t chunk_elems, uint32_t comm_adr, uint32_t dpcfg_adr, uint32_t *status_dev,
                                   cudaStream_t stream);
+
+// the reference's vadd_put: src + 1 is pushed tile by tile into stream `stream_id` of rank `dst_rank` while computing
+cudaError_t launch_vadd_put(CudaDevice &dev, uint64_t src_off, uint32_t count, uint32_t dst_rank, uint32_t stream_id,
+                            uint32_t *status_dev, cudaStream_t stream);
+// consumer of a stream: `count` fp32 of stream `stream_id` -> heap offset dst_off
+cudaError_t launch_stream_pull(CudaDevice &dev, uint64_t dst_off, uint32_t count, uint32_t stream_id, uint32_t *status_dev,
+                               cudaStream_t stream);
 
 // user kernel in the stream path: pulls `count` fp32 from this rank's stream FIFO, optionally adds one,
 // pushes them back (reference kernels/plugins/loopback).  scratch_off: heap scratch of count * 4 bytes.

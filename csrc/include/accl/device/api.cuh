@@ -32,15 +32,16 @@ public:
   // comm_adr / dpcfg_adr: ACCL::get_communicator_addr / get_arithmetic_config_addr
   __device__ Command(void *heap_base, uint32_t comm_adr, uint32_t dpcfg_adr, uint32_t cflags = 0, uint32_t sflags = 0)
       : ctrl_(static_cast<cuda::Ctrl *>(heap_base)),
+        ring_(reinterpret_cast<cuda::EngineArea *>(static_cast<char *>(heap_base) + cuda::CTRL_BYTES / 2)),
         comm_((comm_adr - exchmem::COMM_BASE) / exchmem::COMM_STRIDE), dpcfg_(dpcfg_adr), cflags_(cflags), sflags_(sflags) {}
 
   // Call from ONE thread.  Returns the ticket to pass to finalize_call.
   __device__ Ticket start_call(uint32_t scenario, uint32_t len, uint32_t comm, uint32_t root_src_dst, uint32_t function,
                                uint32_t tag, uint32_t datapath_cfg, uint32_t compression_flags, uint32_t stream_flags,
                                uint64_t addra, uint64_t addrb, uint64_t addrc) {
-    const Ticket t = atomicAdd(&ctrl_->dev_tail, 1ull);
+    const Ticket t = atomicAdd(&ctrl_->cmd_tail, 1ull);
     // ring full: wait until the engine has consumed the entry that used this slot
-    while (t >= dev::ld_acquire_sys(&ctrl_->dev_fetched) + cuda::RING_SLOTS) dev::nanosleep(200);
+    while (t >= dev::ld_acquire_sys(&ctrl_->cmd_fetched) + cuda::RING_SLOTS) dev::nanosleep(200);
     CallDesc d;
     d.scenario = scenario;
     d.count = len;
@@ -55,15 +56,18 @@ public:
     d.set_addr(1, addrb);
     d.set_addr(2, addrc);
     d.aux = 0;
-    ctrl_->dev_ring[t % cuda::RING_SLOTS] = d;
+    cuda::WorkItem *slot = &ring_->cmd_ring[t % cuda::RING_SLOTS].item;
+    slot->desc = d;
+    slot->flags = 0; // not planned: the engine's control CTA decodes and plans the descriptor
+    slot->hc_ptr = 0;
     __threadfence();
-    dev::st_release_sys(&ctrl_->dev_ready[t % cuda::RING_SLOTS], t + 1);
+    dev::st_release_sys(&ctrl_->cmd_ready[t % cuda::RING_SLOTS], t + 1);
     return t + 1;
   }
 
   // Blocks until the engine has retired the call; returns its error word.
   __device__ uint32_t finalize_call(Ticket ticket) {
-    const unsigned long long *st = &ctrl_->dev_status[(ticket - 1) % cuda::RING_SLOTS];
+    const unsigned long long *st = &ctrl_->cmd_status[(ticket - 1) % cuda::RING_SLOTS];
     unsigned long long v;
     uint32_t spins = 0;
     while (((v = dev::ld_acquire_sys(st)) & 0xFFFFFFFFull) != (ticket & 0xFFFFFFFFull))
@@ -113,10 +117,21 @@ public:
   __device__ uint32_t barrier() { return run(operation::barrier, 0, 0, 0, TAG_ANY, 0, 0, 0); }
   __device__ uint32_t nop() { return run(operation::nop, 0, 0, 0, TAG_ANY, 0, 0, 0); }
 
-  // asynchronous flavour: issue now, finalize later (lets a kernel overlap compute)
+  // asynchronous flavours: issue now, finalize later (lets a kernel overlap compute with the collective)
   __device__ Ticket all_reduce_async(uint32_t len, reduceFunction fn, uint64_t src, uint64_t dst) {
     return start_call(static_cast<uint32_t>(operation::allreduce), len, comm_, 0, static_cast<uint32_t>(fn), TAG_ANY, dpcfg_,
                       cflags_, sflags_, src, 0, dst);
+  }
+  __device__ Ticket reduce_scatter_async(uint32_t len, reduceFunction fn, uint64_t src, uint64_t dst) {
+    return start_call(static_cast<uint32_t>(operation::reduce_scatter), len, comm_, 0, static_cast<uint32_t>(fn), TAG_ANY, dpcfg_,
+                      cflags_, sflags_, src, 0, dst);
+  }
+  // non-blocking probe of an asynchronous call: true once retired (then *retcode holds the error word)
+  __device__ bool test_call(Ticket ticket, uint32_t *retcode) {
+    const unsigned long long v = dev::ld_acquire_sys(&ctrl_->cmd_status[(ticket - 1) % cuda::RING_SLOTS]);
+    if ((v & 0xFFFFFFFFull) != (ticket & 0xFFFFFFFFull)) return false;
+    *retcode = static_cast<uint32_t>(v >> 32);
+    return true;
   }
 
 private:
@@ -125,16 +140,19 @@ private:
     return finalize_call(start_call(static_cast<uint32_t>(op), len, comm_, root, fn, tag, dpcfg_, cflags_, sflags_, a, b, c));
   }
   cuda::Ctrl *ctrl_;
+  cuda::EngineArea *ring_;
   uint32_t comm_, dpcfg_, cflags_, sflags_;
 };
 
-// Data port of a user kernel: the rank's stream FIFO (reference ACCLData, accl_hls.h:455-541: push / pull
-// of 64-byte words on the streams between the user kernel and the CCLO).  The FIFO is a byte ring in the
+// Data port of a user kernel: one of the rank's stream FIFOs (reference ACCLData, accl_hls.h:455-541: push / pull
+// of 64-byte words on the streams between the user kernel and the CCLO, routed by TDEST = stream id,
+// dma_mover.cpp:312,644).  Stream id s is served by FIFO s % N_STRM_PORTS, so consumers of different ids do
+// not interleave; id 0 = the default port of stream operands without an id.  A FIFO is a byte ring in the
 // symmetric heap; `push` may target a peer's ring (what `stream_put` lowers to).  All methods are
 // cooperative over ONE CTA (every thread of the block must call them with the same arguments).
 class Data {
 public:
-  __device__ explicit Data(const cuda::DevWorld &w) : w_(w) {}
+  __device__ explicit Data(const cuda::DevWorld &w, uint32_t stream_id = 0) : w_(w), port_(stream_id % cuda::N_STRM_PORTS) {}
 
   // Wait for `bytes` in my FIFO and copy them to dst (any address space visible to the GPU).
   // Returns 0 or KRNL_TIMEOUT_STS_ERROR.
@@ -144,13 +162,14 @@ public:
     __shared__ unsigned long long s_tail;
     __shared__ int s_ok;
     __syncthreads();
+    cuda::StrmPort *sp = &me->strm[port_];
     if (threadIdx.x == 0) {
-      s_tail = me->strm_tail;
-      s_ok = wait_ge(&me->strm_head, s_tail + bytes, timeout_ns) ? 1 : 0;
+      s_tail = sp->tail;
+      s_ok = wait_ge(&sp->head, s_tail + bytes, timeout_ns) ? 1 : 0;
     }
     __syncthreads();
     if (!s_ok) return KRNL_TIMEOUT_STS_ERROR;
-    const char *fifo = heap + w_.strm_off;
+    const char *fifo = heap + w_.strm_off + static_cast<uint64_t>(port_) * w_.strm_cap;
     char *d = static_cast<char *>(dst);
     const unsigned long long tail = s_tail;
     const uint64_t mask = w_.strm_cap - 1;
@@ -162,7 +181,7 @@ public:
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) dev::st_release_sys(&me->strm_tail, tail + bytes);
+    if (threadIdx.x == 0) dev::st_release_sys(&sp->tail, tail + bytes);
     return 0;
   }
 
@@ -171,19 +190,19 @@ public:
   __device__ uint32_t push(const void *src, uint64_t bytes, int dst_rank = -1, uint64_t timeout_ns = 10ull * 1000 * 1000 * 1000) {
     const uint32_t dr = dst_rank < 0 ? w_.rank : static_cast<uint32_t>(dst_rank);
     char *dheap = w_.window + static_cast<uint64_t>(dr) * w_.heap_bytes;
-    cuda::Ctrl *dc = reinterpret_cast<cuda::Ctrl *>(dheap);
+    cuda::StrmPort *dp = &reinterpret_cast<cuda::Ctrl *>(dheap)->strm[port_];
     __shared__ unsigned long long s_start;
     __shared__ int s_ok;
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long start;
       asm volatile("atom.relaxed.sys.global.add.u64 %0, [%1], %2;"
-                   : "=l"(start) : "l"(&dc->strm_reserve), "l"(static_cast<unsigned long long>(bytes)) : "memory");
+                   : "=l"(start) : "l"(&dp->reserve), "l"(static_cast<unsigned long long>(bytes)) : "memory");
       s_start = start;
       s_ok = bytes <= w_.strm_cap;
       uint32_t spins = 0;
       uint64_t t0 = 0;
-      while (s_ok && start + bytes > dev::ld_acquire_sys(&dc->strm_tail) + w_.strm_cap) {
+      while (s_ok && start + bytes > dev::ld_acquire_sys(&dp->tail) + w_.strm_cap) {
         if (++spins > 16) dev::nanosleep(200);
         if ((spins & 0xFF) == 0) {
           const uint64_t now = dev::globaltimer_ns();
@@ -193,7 +212,7 @@ public:
       }
     }
     __syncthreads();
-    char *fifo = dheap + w_.strm_off;
+    char *fifo = dheap + w_.strm_off + static_cast<uint64_t>(port_) * w_.strm_cap;
     const char *s = static_cast<const char *>(src);
     const unsigned long long start = s_start;
     const uint64_t mask = w_.strm_cap - 1;
@@ -210,8 +229,8 @@ public:
     __syncthreads();
     if (threadIdx.x == 0) {
       // publish in reservation order (even after a timeout, so later producers are not blocked forever)
-      wait_ge(&dc->strm_head, start, timeout_ns);
-      dev::st_release_sys(&dc->strm_head, start + bytes);
+      wait_ge(&dp->head, start, timeout_ns);
+      dev::st_release_sys(&dp->head, start + bytes);
     }
     return ok ? 0u : static_cast<uint32_t>(KRNL_TIMEOUT_STS_ERROR);
   }
@@ -219,7 +238,7 @@ public:
   // bytes currently readable in my FIFO (one thread)
   __device__ uint64_t available() const {
     const cuda::Ctrl *me = reinterpret_cast<const cuda::Ctrl *>(w_.window + static_cast<uint64_t>(w_.rank) * w_.heap_bytes);
-    return dev::ld_acquire_sys(&me->strm_head) - dev::ld_acquire_sys(&me->strm_tail);
+    return dev::ld_acquire_sys(&me->strm[port_].head) - dev::ld_acquire_sys(&me->strm[port_].tail);
   }
 
 private:
@@ -237,6 +256,7 @@ private:
     return true;
   }
   cuda::DevWorld w_;
+  uint32_t port_;
 };
 
 } // namespace device

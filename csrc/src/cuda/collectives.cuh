@@ -18,7 +18,7 @@ namespace cuda {
 namespace k {
 
 // ---------------------------------------------------------------- helpers
-__device__ __forceinline__ uint32_t esize(uint32_t dtype) { return dtype_bytes(static_cast<dataType>(dtype)); }
+__device__ __forceinline__ uint32_t esize(uint32_t dtype) { return esize_of(dtype); }
 __device__ __forceinline__ bool is_fp8_dt(uint32_t dtype) {
   return dtype == static_cast<uint32_t>(dataType::float8_e4m3) || dtype == static_cast<uint32_t>(dataType::float8_e5m2);
 }
@@ -457,187 +457,196 @@ __device__ __forceinline__ void fill_table(const Ctx &c, const uint64_t *s_off0,
 // allreduce, two-shot.  NVLS: the switch reduces my shard (multimem.ld_reduce)
 // and broadcasts it (multimem.st).  P2P: pull my shard from every peer,
 // reduce on the SM, store it into every peer's destination.
-__device__ __noinline__ void rv_allreduce(const Ctx &c, uint64_t *s_off0, uint64_t *s_off2) {
+// `rvb_*` are the wait-free data phases (between the entry and the exit meeting): the direct-launch kernel
+// brackets them with chan_sync, the persistent engine runs them as moves on its worker CTAs.
+__device__ __noinline__ void rvb_allreduce(const Ctx &c, const uint64_t *s_off0, const uint64_t *s_off2) {
   const WorkItem &it = c.it;
   const uint32_t P = c.P(), me = c.r();
   const uint32_t dt = it.udtype;
   const size_t count = it.desc.count, es = esize(dt);
-  chan_sync(c, true, it.desc.addr0(), it.desc.addr2(), s_off0, s_off2);
-  if (*c.err == 0) {
-    const size_t per_vec = 16 / es;
-    const size_t nvec = count / per_vec;
-    const size_t shard = (nvec + P - 1) / P;
-    const size_t v0 = static_cast<size_t>(me) * shard < nvec ? static_cast<size_t>(me) * shard : nvec;
-    const size_t v1 = v0 + shard < nvec ? v0 + shard : nvec;
-    const NvOp nop = nvls_op(dt, it.desc.function);
-    const bool sym = all_equal(s_off0, P) && all_equal(s_off2, P) && (s_off0[0] & 15) == 0 && (s_off2[0] & 15) == 0;
-#ifdef ACCL_EXPERIMENTAL_HYBRID_AR
-    // EXPERIMENTAL (compiled out by default, not yet validated on hardware; docs/roadmap.md #5b): the switch
-    // serves multimem.ld_reduce at ~540 GB/s per port while the links carry ~770: give ACCL_HYBRID_P2P_16THS / 16
-    // of my shard (and of the channels) to the peer two-shot body so both limits are used at once.
-#ifndef ACCL_HYBRID_P2P_16THS
-#define ACCL_HYBRID_P2P_16THS 3
-#endif
-    if ((it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && nop != NvOp::none && sym && c.nctas >= 16 && v1 - v0 >= (1u << 16)) {
-      const int n_p2p = c.nctas * ACCL_HYBRID_P2P_16THS / 16 > 0 ? c.nctas * ACCL_HYBRID_P2P_16THS / 16 : 1;
-      const int n_nv = c.nctas - n_p2p;
-      const size_t vm = v1 - (v1 - v0) * ACCL_HYBRID_P2P_16THS / 16;
-      if (c.cta < n_nv) {
-        nvls_reduce_dispatch<true>(nop, c.w.mc + s_off0[0], c.w.mc + s_off2[0], v0, vm, c.cta, n_nv);
-      } else {
-        fill_table(c, s_off0, s_off2, vm * 16, vm * 16, true);
-        reduce_dispatch(c.tab, static_cast<int>(P), static_cast<int>(P), (v1 - vm) * per_vec, dt, it.desc.function, c.cta - n_nv,
-                        n_p2p, c.err);
-      }
-    } else
-#endif
-    if ((it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && nop != NvOp::none && sym) {
-      nvls_reduce_dispatch<true>(nop, c.w.mc + s_off0[0], c.w.mc + s_off2[0], v0, v1, c.cta, c.nctas);
+  const size_t per_vec = 16 / es;
+  const size_t nvec = count / per_vec;
+  const size_t shard = (nvec + P - 1) / P;
+  const size_t v0 = static_cast<size_t>(me) * shard < nvec ? static_cast<size_t>(me) * shard : nvec;
+  const size_t v1 = v0 + shard < nvec ? v0 + shard : nvec;
+  const NvOp nop = nvls_op(dt, it.desc.function);
+  const bool sym = all_equal(s_off0, P) && all_equal(s_off2, P) && (s_off0[0] & 15) == 0 && (s_off2[0] & 15) == 0;
+  const bool nv = (it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && nop != NvOp::none && sym;
+  const uint32_t h16 = it.tune.hybrid_16ths;
+  if (nv && h16 && h16 < 16 && c.nctas >= 16 && v1 - v0 >= (1u << 16)) {
+    // hybrid: the switch serves multimem.ld_reduce below the rate the links carry plain peer traffic at
+    // (profiles/SWEEPS.md): h16 / 16 of my shard (and of the channels) go through the peer two-shot body so
+    // both limits are used at once
+    const int n_p2p = c.nctas * static_cast<int>(h16) / 16 > 0 ? c.nctas * static_cast<int>(h16) / 16 : 1;
+    const int n_nv = c.nctas - n_p2p;
+    const size_t vm = v1 - (v1 - v0) * h16 / 16;
+    if (c.cta < n_nv) {
+      nvls_reduce_dispatch<true>(nop, it.tune.nvls_unroll, c.w.mc + s_off0[0], c.w.mc + s_off2[0], v0, vm, c.cta, n_nv);
     } else {
-      fill_table(c, s_off0, s_off2, v0 * 16, v0 * 16, true);
-      reduce_dispatch(c.tab, static_cast<int>(P), static_cast<int>(P), (v1 - v0) * per_vec, dt, it.desc.function, c.cta,
-                      c.nctas, c.err);
+      fill_table(c, s_off0, s_off2, vm * 16, vm * 16, true);
+      reduce_dispatch(c.tab, static_cast<int>(P), static_cast<int>(P), (v1 - vm) * per_vec, dt, it.desc.function, c.cta - n_nv,
+                      n_p2p, c.err);
     }
-    // sub-vector tail: communicator rank 0 handles it element-wise for everybody
-    const size_t tail0 = nvec * per_vec;
-    if (tail0 < count && me == 0 && c.cta == 0) {
-      fill_table(c, s_off0, s_off2, tail0 * es, tail0 * es, false);
-      reduce_dispatch(c.tab, static_cast<int>(P), static_cast<int>(P), count - tail0, dt, it.desc.function, 0, 1, c.err);
-    }
+  } else if (nv) {
+    nvls_reduce_dispatch<true>(nop, it.tune.nvls_unroll, c.w.mc + s_off0[0], c.w.mc + s_off2[0], v0, v1, c.cta, c.nctas);
+  } else {
+    fill_table(c, s_off0, s_off2, v0 * 16, v0 * 16, true);
+    reduce_dispatch(c.tab, static_cast<int>(P), static_cast<int>(P), (v1 - v0) * per_vec, dt, it.desc.function, c.cta,
+                    c.nctas, c.err);
   }
+  // sub-vector tail: communicator rank 0 handles it element-wise for everybody
+  const size_t tail0 = nvec * per_vec;
+  if (tail0 < count && me == 0 && c.cta == 0) {
+    fill_table(c, s_off0, s_off2, tail0 * es, tail0 * es, false);
+    reduce_dispatch(c.tab, static_cast<int>(P), static_cast<int>(P), count - tail0, dt, it.desc.function, 0, 1, c.err);
+  }
+}
+
+__device__ __noinline__ void rv_allreduce(const Ctx &c, uint64_t *s_off0, uint64_t *s_off2) {
+  chan_sync(c, true, c.it.desc.addr0(), c.it.desc.addr2(), s_off0, s_off2);
+  if (*c.err == 0) rvb_allreduce(c, s_off0, s_off2);
   chan_sync(c, false, 0, 0, nullptr, nullptr);
 }
 
 // every rank pulls everything and reduces locally: no second hop, for
 // messages too big for the slots but small enough that latency dominates
-__device__ __noinline__ void rv_allreduce_oneshot(const Ctx &c, uint64_t *s_off0, uint64_t *s_off2) {
+__device__ __noinline__ void rvb_allreduce_oneshot(const Ctx &c, const uint64_t *s_off0, const uint64_t *s_off2) {
   const WorkItem &it = c.it;
   const uint32_t P = c.P();
-  chan_sync(c, true, it.desc.addr0(), it.desc.addr2(), s_off0, s_off2);
-  if (*c.err == 0) {
-    const NvOp nop = nvls_op(it.udtype, it.desc.function);
-    const size_t es = esize(it.udtype), per_vec = 16 / es, nvec = it.desc.count / per_vec;
-    const bool sym = all_equal(s_off0, P) && (s_off0[0] & 15) == 0 && (it.desc.addr2() & 15) == 0;
-    size_t done = 0;
-    if ((it.flags & WF_USE_MC) && nop != NvOp::none && sym) {
-      nvls_reduce_dispatch<false>(nop, c.w.mc + s_off0[0], c.heap(c.w.rank) + it.desc.addr2(), 0, nvec, c.cta, c.nctas);
-      done = nvec * per_vec;
-    }
-    if (done < it.desc.count) {
-      fill_table(c, s_off0, nullptr, done * es, 0, false); // communicator-rank order: identical sums everywhere
-      if (threadIdx.x == 0) c.tab->dst[0] = c.heap(c.w.rank) + it.desc.addr2() + done * es;
-      __syncthreads();
-      reduce_dispatch(c.tab, static_cast<int>(P), 1, it.desc.count - done, it.udtype, it.desc.function, c.cta, c.nctas, c.err);
-    }
+  // In place on ANY rank (source == destination): that rank's result stores would race with the peers' reads of
+  // its source.  The exchanged offsets are identical everywhere, so all ranks take the two-shot body together
+  // (only a shard's owner writes it, after having read it).
+  bool inplace = false;
+  for (uint32_t q = 0; q < P; ++q) inplace = inplace || s_off0[q] == s_off2[q];
+  if (inplace) {
+    rvb_allreduce(c, s_off0, s_off2);
+    return;
   }
+  const NvOp nop = nvls_op(it.udtype, it.desc.function);
+  const size_t es = esize(it.udtype), per_vec = 16 / es, nvec = it.desc.count / per_vec;
+  const bool sym = all_equal(s_off0, P) && (s_off0[0] & 15) == 0 && (it.desc.addr2() & 15) == 0;
+  size_t done = 0;
+  if ((it.flags & WF_USE_MC) && nop != NvOp::none && sym) {
+    nvls_reduce_dispatch<false>(nop, it.tune.nvls_unroll, c.w.mc + s_off0[0], c.heap(c.w.rank) + it.desc.addr2(), 0, nvec, c.cta, c.nctas);
+    done = nvec * per_vec;
+  }
+  if (done < it.desc.count) {
+    fill_table(c, s_off0, nullptr, done * es, 0, false); // communicator-rank order: identical sums everywhere
+    if (threadIdx.x == 0) c.tab->dst[0] = c.heap(c.w.rank) + it.desc.addr2() + done * es;
+    __syncthreads();
+    reduce_dispatch(c.tab, static_cast<int>(P), 1, it.desc.count - done, it.udtype, it.desc.function, c.cta, c.nctas, c.err);
+  }
+}
+__device__ __noinline__ void rv_allreduce_oneshot(const Ctx &c, uint64_t *s_off0, uint64_t *s_off2) {
+  chan_sync(c, true, c.it.desc.addr0(), c.it.desc.addr2(), s_off0, s_off2);
+  if (*c.err == 0) rvb_allreduce_oneshot(c, s_off0, s_off2);
   chan_sync(c, false, 0, 0, nullptr, nullptr);
 }
 
-__device__ __noinline__ void rv_reduce_scatter(const Ctx &c, uint64_t *s_off0, uint64_t *s_off2) {
+__device__ __noinline__ void rvb_reduce_scatter(const Ctx &c, const uint64_t *s_off0, const uint64_t *s_off2) {
+  (void)s_off2;
   const WorkItem &it = c.it;
   const uint32_t P = c.P(), me = c.r();
   const size_t count = it.desc.count, es = esize(it.udtype);
-  chan_sync(c, true, it.desc.addr0(), it.desc.addr2(), s_off0, s_off2);
-  if (*c.err == 0) {
-    const size_t blk_bytes = count * es;
-    const NvOp nop = nvls_op(it.udtype, it.desc.function);
-    char *dst = c.heap(c.w.rank) + it.desc.addr2();
-    const bool sym = all_equal(s_off0, P) && ((s_off0[0] + me * blk_bytes) & 15) == 0 && (it.desc.addr2() & 15) == 0;
-    size_t done = 0;
-    if ((it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && nop != NvOp::none && sym) {
-      const size_t nvec = blk_bytes / 16;
-      nvls_reduce_dispatch<false>(nop, c.w.mc + s_off0[0] + me * blk_bytes, dst, 0, nvec, c.cta, c.nctas);
-      done = nvec * 16 / es;
-    }
-    if (done < count) {
-      fill_table(c, s_off0, nullptr, me * blk_bytes + done * es, 0, true);
-      if (threadIdx.x == 0) c.tab->dst[0] = dst + done * es;
-      __syncthreads();
-      reduce_dispatch(c.tab, static_cast<int>(P), 1, count - done, it.udtype, it.desc.function, c.cta, c.nctas, c.err);
-    }
+  const size_t blk_bytes = count * es;
+  const NvOp nop = nvls_op(it.udtype, it.desc.function);
+  char *dst = c.heap(c.w.rank) + it.desc.addr2();
+  const bool sym = all_equal(s_off0, P) && ((s_off0[0] + me * blk_bytes) & 15) == 0 && (it.desc.addr2() & 15) == 0;
+  size_t done = 0;
+  if ((it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && nop != NvOp::none && sym) {
+    const size_t nvec = blk_bytes / 16;
+    nvls_reduce_dispatch<false>(nop, it.tune.nvls_unroll, c.w.mc + s_off0[0] + me * blk_bytes, dst, 0, nvec, c.cta, c.nctas);
+    done = nvec * 16 / es;
   }
+  if (done < count) {
+    fill_table(c, s_off0, nullptr, me * blk_bytes + done * es, 0, true);
+    if (threadIdx.x == 0) c.tab->dst[0] = dst + done * es;
+    __syncthreads();
+    reduce_dispatch(c.tab, static_cast<int>(P), 1, count - done, it.udtype, it.desc.function, c.cta, c.nctas, c.err);
+  }
+}
+__device__ __noinline__ void rv_reduce_scatter(const Ctx &c, uint64_t *s_off0, uint64_t *s_off2) {
+  chan_sync(c, true, c.it.desc.addr0(), c.it.desc.addr2(), s_off0, s_off2);
+  if (*c.err == 0) rvb_reduce_scatter(c, s_off0, s_off2);
   chan_sync(c, false, 0, 0, nullptr, nullptr);
 }
 
 __device__ __noinline__ void rv_bcast_pipelined(const Ctx &c, const uint64_t *s_off);
-#ifdef ACCL_EXPERIMENTAL_BCAST_FLAGS
 __device__ __noinline__ void rv_bcast_flags(const Ctx &c, const uint64_t *s_off);
-#endif
 
-// push-style data movement shared by allgather / bcast / scatter / gather / alltoall
-__device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_off0, uint64_t *s_off2) {
+// push-style data movement shared by allgather / bcast / scatter / gather / alltoall.
+// `stepwise_ok`: the caller can run the pipelined broadcasts, which meet the peers between chunks (direct launches
+// only: inside the engine every wait must be a parked step, so it takes the single-pass bodies).
+__device__ __noinline__ void rvb_move(const Ctx &c, EgrPattern pat, const uint64_t *s_off0, const uint64_t *s_off2, bool stepwise_ok) {
+  (void)s_off0;
   const WorkItem &it = c.it;
   const uint32_t P = c.P(), me = c.r(), root = it.desc.root_src_dst;
   const size_t blk = static_cast<size_t>(it.desc.count) * esize(it.udtype);
-  // bcast keeps its buffer in addr0 on every rank; the others receive into addr2
-  const uint64_t my_dst = pat == EP_BCAST ? it.desc.addr0() : it.desc.addr2();
-  chan_sync(c, true, it.desc.addr0(), my_dst, s_off0, s_off2);
-  if (*c.err == 0) {
-    const char *src = c.heap(c.w.rank) + it.desc.addr0();
-    const bool mc_ok = (it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && all_equal(s_off2, P) && (blk & 15) == 0 &&
-                       (s_off2[0] & 15) == 0 && (it.desc.addr0() & 15) == 0;
-    bool bcast_pipelined = pat == EP_BCAST && P >= 3 && blk >= (128u << 20) && (blk & 15) == 0;
-    for (uint32_t q = 0; q < P; ++q) bcast_pipelined = bcast_pipelined && (s_off2[q] & 15) == 0;
-    switch (pat) {
-    case EP_ALLGATHER:
-      if (mc_ok) {
-        nvls_bcast_range(src, c.w.mc + s_off2[0] + me * blk, blk / 16, c.cta, c.nctas);
-      } else {
-        fill_table(c, nullptr, s_off2, 0, me * blk, true);
-        if (threadIdx.x == 0) c.tab->src[0] = src;
-        __syncthreads();
-        copy_dispatch(c.tab, static_cast<int>(P), blk, c.cta, c.nctas);
-      }
-      break;
-    case EP_BCAST:
-      if (bcast_pipelined) {
-#ifdef ACCL_EXPERIMENTAL_BCAST_FLAGS
-        rv_bcast_flags(c, s_off2);
-#else
-        rv_bcast_pipelined(c, s_off2);
-#endif
-      } else if (me == root) {
-        if (mc_ok) {
-          // the multicast store also rewrites the root's own copy with identical bytes
-          nvls_bcast_range(src, c.w.mc + s_off2[0], blk / 16, c.cta, c.nctas);
-        } else {
-          fill_table(c, nullptr, s_off2, 0, 0, true); // dst[0] is my own buffer: skip it
-          if (threadIdx.x == 0) {
-            c.tab->src[0] = src;
-            for (uint32_t k = 1; k < P; ++k) c.tab->dst[k - 1] = c.tab->dst[k];
-          }
-          __syncthreads();
-          copy_dispatch(c.tab, static_cast<int>(P) - 1, blk, c.cta, c.nctas);
-        }
-      }
-      break;
-    case EP_SCATTER:
-      if (me == root)
-        for (uint32_t k = 0; k < P; ++k) {
-          // CTAs visit the destinations in different orders: all P switch ports are fed at once
-          // instead of bursting one block at a time into a single port
-          const uint32_t q = (me + k + static_cast<uint32_t>(c.cta)) % P;
-          copy_simple(c.heap(c.g(q)) + s_off2[q], src + q * blk, blk, c.cta, c.nctas);
-        }
-      break;
-    case EP_GATHER:
-      copy_simple(c.heap(c.g(root)) + s_off2[root] + me * blk, src, blk, c.cta, c.nctas);
-      break;
-    case EP_ALLTOALL:
-      for (uint32_t k = 0; k < P; ++k) {
-        const uint32_t q = (me + k + static_cast<uint32_t>(c.cta)) % P;
-        copy_simple(c.heap(c.g(q)) + s_off2[q] + me * blk, src + q * blk, blk, c.cta, c.nctas);
-      }
-      break;
-    default: break;
+  const char *src = c.heap(c.w.rank) + it.desc.addr0();
+  const bool mc_ok = (it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && all_equal(s_off2, P) && (blk & 15) == 0 &&
+                     (s_off2[0] & 15) == 0 && (it.desc.addr0() & 15) == 0;
+  bool bcast_pipelined = stepwise_ok && pat == EP_BCAST && P >= 3 && blk >= (128u << 20) && (blk & 15) == 0;
+  for (uint32_t q = 0; q < P; ++q) bcast_pipelined = bcast_pipelined && (s_off2[q] & 15) == 0;
+  switch (pat) {
+  case EP_ALLGATHER:
+    if (mc_ok) {
+      nvls_bcast_range(src, c.w.mc + s_off2[0] + me * blk, blk / 16, c.cta, c.nctas);
+    } else {
+      fill_table(c, nullptr, s_off2, 0, me * blk, true);
+      if (threadIdx.x == 0) c.tab->src[0] = src;
+      __syncthreads();
+      copy_dispatch(c.tab, static_cast<int>(P), blk, c.cta, c.nctas);
     }
+    break;
+  case EP_BCAST:
+    if (bcast_pipelined) {
+      if (it.tune.bcast_flags) rv_bcast_flags(c, s_off2);
+      else rv_bcast_pipelined(c, s_off2);
+    } else if (me == root) {
+      if (mc_ok) {
+        // the multicast store also rewrites the root's own copy with identical bytes
+        nvls_bcast_range(src, c.w.mc + s_off2[0], blk / 16, c.cta, c.nctas);
+      } else {
+        fill_table(c, nullptr, s_off2, 0, 0, true); // dst[0] is my own buffer: skip it
+        if (threadIdx.x == 0) {
+          c.tab->src[0] = src;
+          for (uint32_t k = 1; k < P; ++k) c.tab->dst[k - 1] = c.tab->dst[k];
+        }
+        __syncthreads();
+        copy_dispatch(c.tab, static_cast<int>(P) - 1, blk, c.cta, c.nctas);
+      }
+    }
+    break;
+  case EP_SCATTER:
+    if (me == root)
+      for (uint32_t k = 0; k < P; ++k) {
+        // CTAs visit the destinations in different orders: all P switch ports are fed at once
+        // instead of bursting one block at a time into a single port
+        const uint32_t q = (me + k + static_cast<uint32_t>(c.cta)) % P;
+        copy_simple(c.heap(c.g(q)) + s_off2[q], src + q * blk, blk, c.cta, c.nctas);
+      }
+    break;
+  case EP_GATHER:
+    copy_simple(c.heap(c.g(root)) + s_off2[root] + me * blk, src, blk, c.cta, c.nctas);
+    break;
+  case EP_ALLTOALL:
+    for (uint32_t k = 0; k < P; ++k) {
+      const uint32_t q = (me + k + static_cast<uint32_t>(c.cta)) % P;
+      copy_simple(c.heap(c.g(q)) + s_off2[q] + me * blk, src + q * blk, blk, c.cta, c.nctas);
+    }
+    break;
+  default: break;
   }
+}
+__device__ __noinline__ void rv_move(const Ctx &c, EgrPattern pat, uint64_t *s_off0, uint64_t *s_off2) {
+  // bcast keeps its buffer in addr0 on every rank; the others receive into addr2
+  const uint64_t my_dst = pat == EP_BCAST ? c.it.desc.addr0() : c.it.desc.addr2();
+  chan_sync(c, true, c.it.desc.addr0(), my_dst, s_off0, s_off2);
+  if (*c.err == 0) rvb_move(c, pat, s_off0, s_off2, true);
   chan_sync(c, false, 0, 0, nullptr, nullptr);
 }
 
-#ifdef ACCL_EXPERIMENTAL_REDUCE_PUSH
-// EXPERIMENTAL (not compiled by default, not yet validated on hardware; docs/roadmap.md #1).
-// Write-only rooted reduce: the message is cut into P-1 slices (one per non-root "worker") and every CTA
+// Write-only rooted reduce (tune.reduce_push): the message is cut into P-1 slices (one per non-root "worker") and every CTA
 // owns a stripe of every slice, processed in chunks of CH vectors.  In step st every rank PUSHES its chunk
 // st of slice j into worker j's scratch (stage st & 1, one region per source), and worker j reduces chunk
 // st - 1 from its P-1 scratch regions plus its own operand, storing the result straight into the root's
@@ -702,57 +711,53 @@ __device__ __noinline__ size_t rv_reduce_push(const Ctx &c, const uint64_t *s_of
   }
   return nvec;
 }
-#endif
 
 // reduce to root.  Small: the root pulls (or lets the switch reduce) everything.  Large
 // (P >= 3): the P-1 other ranks each reduce one slice and store it into the root's buffer,
 // so the root's inbound link carries N bytes instead of (P-1) N.
-__device__ __noinline__ void rv_reduce(const Ctx &c, uint64_t *s_off0, uint64_t *s_off2) {
+__device__ __noinline__ void rvb_reduce(const Ctx &c, const uint64_t *s_off0, const uint64_t *s_off2, bool stepwise_ok) {
   const WorkItem &it = c.it;
   const uint32_t P = c.P(), me = c.r(), root = it.desc.root_src_dst;
-  chan_sync(c, true, it.desc.addr0(), it.desc.addr2(), s_off0, s_off2);
-  if (*c.err == 0) {
-    const size_t es = esize(it.udtype), count = it.desc.count;
-    const NvOp nop = nvls_op(it.udtype, it.desc.function);
-    const bool sym = all_equal(s_off0, P) && (s_off0[0] & 15) == 0 && (s_off2[root] & 15) == 0;
-    const bool use_mc = (it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && nop != NvOp::none && sym;
-    char *root_dst = c.heap(c.g(root)) + s_off2[root];
-    const size_t nvec = count * es / 16;
-    const bool distributed = P >= 3 && count * es >= (1u << 20) && (s_off2[root] & 15) == 0;
-    size_t done = 0;
-#ifdef ACCL_EXPERIMENTAL_REDUCE_PUSH
-    // all ranks take the same decision: it only depends on the call and on the (identical) geometry
-    if (distributed && count * es >= (8u << 20) && all_aligned16(s_off0, P)) done = rv_reduce_push(c, s_off0, s_off2) * 16 / es;
-    if (done) {
-      // handled above; the sub-vector tail (if any) is reduced by the root below
-    } else
-#endif
-    if (distributed) {
-      if (me != root) {
-        const uint32_t j = (me + P - root - 1) % P; // my index among the P-1 workers
-        const size_t per = (nvec + (P - 1) - 1) / (P - 1);
-        const size_t v0 = j * per < nvec ? j * per : nvec, v1 = v0 + per < nvec ? v0 + per : nvec;
-        {
-          // peer pulls: every worker's inbound link carries ~N, like the root's; measured faster than
-          // letting the switch reduce (profiles/SWEEPS.md: multimem.ld_reduce tops out near 470 GB/s here)
-          fill_table(c, s_off0, nullptr, v0 * 16, 0, true);
-          if (threadIdx.x == 0) c.tab->dst[0] = root_dst + v0 * 16;
-          __syncthreads();
-          reduce_dispatch(c.tab, static_cast<int>(P), 1, (v1 - v0) * (16 / es), it.udtype, it.desc.function, c.cta, c.nctas, c.err);
-        }
-      }
-      done = nvec * 16 / es; // the sub-vector tail (if any) is reduced by the root below
-    } else if (me == root && use_mc) {
-      nvls_reduce_dispatch<false>(nop, c.w.mc + s_off0[0], root_dst, 0, nvec, c.cta, c.nctas);
-      done = nvec * 16 / es;
-    }
-    if (me == root && done < count) {
-      fill_table(c, s_off0, nullptr, done * es, 0, false);
-      if (threadIdx.x == 0) c.tab->dst[0] = root_dst + done * es;
+  const size_t es = esize(it.udtype), count = it.desc.count;
+  const NvOp nop = nvls_op(it.udtype, it.desc.function);
+  const bool sym = all_equal(s_off0, P) && (s_off0[0] & 15) == 0 && (s_off2[root] & 15) == 0;
+  const bool use_mc = (it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && nop != NvOp::none && sym;
+  char *root_dst = c.heap(c.g(root)) + s_off2[root];
+  const size_t nvec = count * es / 16;
+  const bool distributed = P >= 3 && count * es >= (1u << 20) && (s_off2[root] & 15) == 0;
+  size_t done = 0;
+  // all ranks take the same decision: it only depends on the call and on the (identical) geometry
+  if (stepwise_ok && it.tune.reduce_push && distributed && count * es >= (8u << 20) && all_aligned16(s_off0, P))
+    done = rv_reduce_push(c, s_off0, s_off2) * 16 / es;
+  if (done) {
+    // handled above; the sub-vector tail (if any) is reduced by the root below
+  } else if (distributed) {
+    if (me != root) {
+      const uint32_t j = (me + P - root - 1) % P; // my index among the P-1 workers
+      const size_t per = (nvec + (P - 1) - 1) / (P - 1);
+      const size_t v0 = j * per < nvec ? j * per : nvec, v1 = v0 + per < nvec ? v0 + per : nvec;
+      // peer pulls: every worker's inbound link carries ~N, like the root's; measured faster than letting the
+      // switch reduce the slices (profiles/SWEEPS.md)
+      fill_table(c, s_off0, nullptr, v0 * 16, 0, true);
+      if (threadIdx.x == 0) c.tab->dst[0] = root_dst + v0 * 16;
       __syncthreads();
-      reduce_dispatch(c.tab, static_cast<int>(P), 1, count - done, it.udtype, it.desc.function, c.cta, c.nctas, c.err);
+      reduce_dispatch(c.tab, static_cast<int>(P), 1, (v1 - v0) * (16 / es), it.udtype, it.desc.function, c.cta, c.nctas, c.err);
     }
+    done = nvec * 16 / es; // the sub-vector tail (if any) is reduced by the root below
+  } else if (me == root && use_mc) {
+    nvls_reduce_dispatch<false>(nop, it.tune.nvls_unroll, c.w.mc + s_off0[0], root_dst, 0, nvec, c.cta, c.nctas);
+    done = nvec * 16 / es;
   }
+  if (me == root && done < count) {
+    fill_table(c, s_off0, nullptr, done * es, 0, false);
+    if (threadIdx.x == 0) c.tab->dst[0] = root_dst + done * es;
+    __syncthreads();
+    reduce_dispatch(c.tab, static_cast<int>(P), 1, count - done, it.udtype, it.desc.function, c.cta, c.nctas, c.err);
+  }
+}
+__device__ __noinline__ void rv_reduce(const Ctx &c, uint64_t *s_off0, uint64_t *s_off2) {
+  chan_sync(c, true, c.it.desc.addr0(), c.it.desc.addr2(), s_off0, s_off2);
+  if (*c.err == 0) rvb_reduce(c, s_off0, s_off2, true);
   chan_sync(c, false, 0, 0, nullptr, nullptr);
 }
 
@@ -811,9 +816,7 @@ __device__ __noinline__ void rv_bcast_pipelined(const Ctx &c, const uint64_t *s_
   }
 }
 
-#ifdef ACCL_EXPERIMENTAL_BCAST_FLAGS
-// EXPERIMENTAL (not compiled by default, not yet validated on hardware; docs/roadmap.md #2).
-// Same deal-and-forward schedule as rv_bcast_pipelined, driven by one-way flags instead of a meeting per
+// tune.bcast_flags: same deal-and-forward schedule as rv_bcast_pipelined, driven by one-way flags instead of a meeting per
 // step: after the stores of a chunk the producer raises a per-(channel, source) counter at the consumer
 // (st.release.sys); the consumer waits for the count it needs (ld.acquire.sys).  The root never waits, a
 // worker waits for the root's chunk before forwarding it and, at the end, for every other worker to have
@@ -844,14 +847,14 @@ __device__ __noinline__ void rv_bcast_flags(const Ctx &c, const uint64_t *s_off)
     __syncthreads();
     if (threadIdx.x == 0) {
       const uint32_t gq = c.g(q);
-      const uint32_t v = c.me->step_sent[ch][gq] + 1;
-      c.me->step_sent[ch][gq] = v;
-      st_release_sys(&c.ctrl(gq)->step_sig[ch][c.w.rank], v);
+      const uint32_t v = c.pads().step_sent[ch][gq] + 1;
+      c.pads().step_sent[ch][gq] = v;
+      st_release_sys(&c.pads_of(gq).step_sig[ch][c.w.rank], v);
     }
   };
   // wait until rank q has delivered `n` chunks of this call to me
   auto await = [&](uint32_t q, uint32_t n) {
-    if (threadIdx.x == 0) wait_ge(&c.me->step_sig[ch][c.g(q)], c.me->step_seen[ch][c.g(q)] + n, c, RECEIVE_TIMEOUT_ERROR);
+    if (threadIdx.x == 0) wait_ge(&c.pads().step_sig[ch][c.g(q)], c.pads().step_seen[ch][c.g(q)] + n, c, RECEIVE_TIMEOUT_ERROR);
     __syncthreads();
   };
   if (me == root) {
@@ -887,13 +890,12 @@ __device__ __noinline__ void rv_bcast_flags(const Ctx &c, const uint64_t *s_off)
     for (uint32_t k = 1; k < W; ++k) await((root + 1 + (j_me + k) % W) % P, steps);
     __syncthreads();
     if (threadIdx.x == 0) {
-      c.me->step_seen[ch][c.g(root)] += steps;
-      for (uint32_t k = 1; k < W; ++k) c.me->step_seen[ch][c.g((root + 1 + (j_me + k) % W) % P)] += steps;
+      c.pads().step_seen[ch][c.g(root)] += steps;
+      for (uint32_t k = 1; k < W; ++k) c.pads().step_seen[ch][c.g((root + 1 + (j_me + k) % W) % P)] += steps;
     }
     __syncthreads();
   }
 }
-#endif
 
 // rendezvous send / recv: a pair of ranks meets on the pads, the receiver
 // announces its buffer, the sender stores straight into it

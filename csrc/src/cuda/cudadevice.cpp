@@ -143,18 +143,23 @@ void CudaRequest::wait() {
     // short spin for latency, then let the driver block on the stream
     const auto t0 = std::chrono::steady_clock::now();
     while (!hc_done(hc, seq)) {
-      if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) {
-        cudaSetDevice(dev->device());
-        cudaError_t e = cudaStreamSynchronize(stream);
-        if (e != cudaSuccess) {
-          complete(DMA_INTERNAL_ERROR, 0);
-          throw std::runtime_error(std::string("CUDA error while waiting for a call: ") + cudaGetErrorString(e));
-        }
-        // the stream has drained: the record must be there (engine mode: the stream waited for it)
-        const auto t1 = std::chrono::steady_clock::now();
-        while (!hc_done(hc, seq) && std::chrono::steady_clock::now() - t1 < std::chrono::seconds(2)) std::this_thread::yield();
-        break;
+      if (std::chrono::steady_clock::now() - t0 <= std::chrono::microseconds(200)) continue;
+      if (unordered) {
+        // engine call that does not hold its stream (asynchronous point to point): it may stay parked for as long
+        // as the peer takes; the engine itself retires it with RECEIVE_TIMEOUT_ERROR when its wait budget is spent
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+        continue;
       }
+      cudaSetDevice(dev->device());
+      cudaError_t e = cudaStreamSynchronize(stream);
+      if (e != cudaSuccess) {
+        complete(DMA_INTERNAL_ERROR, 0);
+        throw std::runtime_error(std::string("CUDA error while waiting for a call: ") + cudaGetErrorString(e));
+      }
+      // the stream has drained: the record must be there (engine mode: the proxy waited for it)
+      const auto t1 = std::chrono::steady_clock::now();
+      while (!hc_done(hc, seq) && std::chrono::steady_clock::now() - t1 < std::chrono::seconds(2)) std::this_thread::yield();
+      break;
     }
     std::atomic_thread_fence(std::memory_order_acquire);
   }
@@ -204,23 +209,41 @@ CudaDevice::CudaDevice(std::shared_ptr<Oob> oob, const CudaConfig &cfg) : oob_(s
   std::memset(hc_host_, 0, sizeof(HostCompletion) * N_REQ_SLOTS);
   ACCL_CUDART(cudaHostGetDevicePointer(reinterpret_cast<void **>(&hc_dev_), hc_host_, 0));
   slot_owner_.assign(N_REQ_SLOTS, nullptr);
-  // device-side stream port: first allocation, so it sits at the same offset in every heap
-  strm_area_ = allocate(STREAM_FIFO_BYTES, bufferKind::p2p);
-  world_.strm_off = strm_area_->device_addr();
-  world_.strm_cap = STREAM_FIFO_BYTES;
-#ifdef ACCL_EXPERIMENTAL_REDUCE_PUSH
+  // Symmetric infrastructure areas: allocated first and in the same order by every rank, so each sits at the same
+  // offset in every heap.  Sizes derive from the heap size (identical everywhere) unless configured.
   {
-    // second allocation: same offset in every heap as well
-    const size_t scr = std::min<size_t>(64u << 20, heap_->bytes() / 8);
+    // device-side stream ports
+    size_t cap = STREAM_FIFO_BYTES;
+    while (cap > (4u << 10) && cap * N_STRM_PORTS > heap_->bytes() / 16) cap >>= 1;
+    strm_area_ = allocate(cap * N_STRM_PORTS, bufferKind::p2p);
+    world_.strm_off = strm_area_->device_addr();
+    world_.strm_cap = cap;
+    // staging of the one-way protocols: [bank][parity][source][region]; budget: an eighth of the heap
+    const size_t regions = static_cast<size_t>(N_BANKS) * 2 * world_.world;
+    const size_t budget = heap_->bytes() / 8 / regions;
+    size_t ll = cfg_.ll_bytes ? cfg_.ll_bytes : std::min<size_t>(512u << 10, budget / 4);
+    size_t stg = cfg_.stage_bytes ? cfg_.stage_bytes : std::min<size_t>(2u << 20, budget - std::min(budget, ll));
+    ll &= ~static_cast<size_t>(4095);
+    stg &= ~static_cast<size_t>(4095);
+    if (ll >= (4u << 10) * STG_CH / 8 && stg >= (4u << 10)) {
+      ll_area_ = allocate(stg_area_bytes(world_.world, ll), bufferKind::p2p);
+      stg_area_ = allocate(stg_area_bytes(world_.world, stg), bufferKind::p2p);
+      world_.ll_off = ll_area_->device_addr();
+      world_.ll_bytes = ll;
+      world_.stg_off = stg_area_->device_addr();
+      world_.stg_bytes = stg;
+    }
+    // scratch of the write-only rooted reduce
+    const size_t scr = std::min<size_t>(64u << 20, heap_->bytes() / 16) & ~static_cast<size_t>(4095);
     scr_area_ = allocate(scr, bufferKind::p2p);
     world_.scr_off = scr_area_->device_addr();
     world_.scr_bytes = scr;
   }
-#endif
+  apply_env_tuning();
   preload_engine_kernels();
   preload_gemm_rs_kernels();
   preload_vadd_kernels();
-  (void)plugin_counter(); // allocate now: cudaMalloc later could stall behind a running engine kernel
+  (void)plugin_scratch(16u << 10); // allocate now: cudaMalloc later could stall behind a running engine kernel
   ACCL_CUDART(launch_reset_ctrl(world_, stream_));
   ACCL_CUDART(cudaStreamSynchronize(stream_));
   oob_->barrier(); // nobody signals a peer whose control block is not zeroed yet
@@ -233,6 +256,9 @@ CudaDevice::~CudaDevice() {
   cudaStreamSynchronize(stream_);
   egr_area_.reset();
   strm_area_.reset();
+  stg_area_.reset();
+  ll_area_.reset();
+  scr_area_.reset();
   slot_owner_.clear();
   if (hc_host_) cudaFreeHost(hc_host_);
   heap_.reset();
@@ -252,16 +278,21 @@ std::string CudaDevice::describe() {
     << (heap_->bytes() >> 20) << " MiB nvls=" << (heap_->has_multicast() ? "yes" : "no");
   if (!heap_->has_multicast()) o << " (" << heap_->multicast_note() << ")";
   o << " mode=" << (cfg_.engine ? "engine" : "direct") << " max_ctas=" << cfg_.max_ctas;
+  if (engine_) o << " engine_workers=" << engine_->workers();
+  o << " staging=" << (world_.stg_bytes >> 10) << "K ll=" << (world_.ll_bytes >> 10) << "K";
   return o.str();
 }
 
-unsigned int *CudaDevice::plugin_counter() {
-  if (!plugin_counter_) {
+void *CudaDevice::plugin_scratch(size_t bytes) {
+  if (bytes > plugin_scratch_bytes_) {
     cudaSetDevice(cfg_.device);
-    ACCL_CUDART(cudaMalloc(&plugin_counter_, 64));
-    ACCL_CUDART(cudaMemset(plugin_counter_, 0, 64));
+    if (plugin_scratch_) throw std::runtime_error("plugin scratch cannot grow while in use");
+    const size_t cap = std::max<size_t>(bytes, 16u << 10);
+    ACCL_CUDART(cudaMalloc(&plugin_scratch_, cap));
+    ACCL_CUDART(cudaMemset(plugin_scratch_, 0, cap));
+    plugin_scratch_bytes_ = cap;
   }
-  return plugin_counter_;
+  return plugin_scratch_;
 }
 
 void CudaDevice::printDebug() { ACCL_ERROR_LOG(debug_state()); }
@@ -277,22 +308,19 @@ std::string CudaDevice::debug_state() {
   for (uint32_t p = 0; p < world_.world; ++p) {
     if (p == world_.rank) continue;
     o << " peer " << p << ":";
-    for (int ch = 0; ch < 4; ++ch)
-      o << " ch" << ch << "[sync sent=" << c->sent[ch][p] << " exp=" << c->expect[ch][p] << " sig=" << c->sig[ch][p]
-        << " | egr sent=" << c->egr_sent[ch][p] << " ack=" << c->egr_ack[ch][p] << " exp=" << c->egr_expect[ch][p]
-        << " sig=" << c->egr_sig[ch][p] << "]";
-    o << "\n";
+    for (int b = 0; b < N_BANKS; ++b) {
+      const PadBank &pb = c->pad[b];
+      const StageBank &sb = c->stg[b];
+      if (!pb.sent[0][p] && !pb.sig[0][p] && !sb.sent[0][p] && !sb.recvd[0][p] && !pb.sent[MAX_CH - 2][p]) continue;
+      o << " bank" << b << "[sync0 sent=" << pb.sent[0][p] << " exp=" << pb.expect[0][p] << " sig=" << pb.sig[0][p]
+        << " | eng sent=" << pb.sent[MAX_CH - 2][p] << " exp=" << pb.expect[MAX_CH - 2][p] << " sig=" << pb.sig[MAX_CH - 2][p]
+        << " | stg0 sent=" << sb.sent[0][p] << " recvd=" << sb.recvd[0][p] << " sig=" << sb.sig[0][p] << " ack=" << sb.ack[0][p] << "]";
+    }
+    o << " egr0[sent=" << c->egr_sent[0][p] << " ack=" << c->egr_ack[0][p] << " exp=" << c->egr_expect[0][p]
+      << " sig=" << c->egr_sig[0][p] << "] notes[posted=" << c->note_posted[p] << "]\n";
   }
-#ifdef ACCL_PHASE_TIMING
-  o << " phase timing (channel 0): calls=" << c->dbg_calls << " kernel_ns=" << c->dbg_kernel_ns << " sync_ns=" << c->dbg_sync_ns
-    << " syncs=" << c->dbg_syncs << " wait_ns=" << c->dbg_wait_ns << " waits=" << c->dbg_waits;
-  if (c->dbg_calls)
-    o << "  per call: kernel " << c->dbg_kernel_ns / c->dbg_calls << " ns, in meetings " << c->dbg_sync_ns / c->dbg_calls
-      << " ns over " << static_cast<double>(c->dbg_syncs) / static_cast<double>(c->dbg_calls) << " meetings; flag waits "
-      << c->dbg_wait_ns / c->dbg_calls << " thread-ns in " << static_cast<double>(c->dbg_waits) / static_cast<double>(c->dbg_calls)
-      << " waits";
-  o << "\n";
-#endif
+  o << " engine: cmd_tail=" << c->cmd_tail << " fetched=" << c->cmd_fetched << " moves=" << c->move_tail
+    << " calls_done=" << c->eng_calls_done << " parks=" << c->eng_parks << "\n";
   return o.str();
 }
 
@@ -370,6 +398,7 @@ uint32_t CudaDevice::host_config(const CallDesc &d) {
     cudaStreamSynchronize(stream_);
     launch_reset_ctrl(world_, stream_);
     cudaStreamSynchronize(stream_);
+    for (auto &r : slot_owner_) r.reset();
     shadow_[exchmem::CFGRDY / 4] = 0;
     shadow_[exchmem::PKT_ENABLED / 4] = 0;
     return 0;
@@ -396,14 +425,88 @@ uint32_t CudaDevice::host_config(const CallDesc &d) {
 
 PlanCfg CudaDevice::plan_cfg() const {
   PlanCfg c;
+  std::memset(&c, 0, sizeof(c));
   c.max_ctas = static_cast<uint32_t>(cfg_.max_ctas);
+  if (engine_) c.max_ctas = std::min<uint32_t>(c.max_ctas, static_cast<uint32_t>(engine_->workers())); // channels == worker CTAs
   c.nvls_min_ranks = static_cast<uint32_t>(cfg_.nvls_min_ranks);
   c.has_mc = heap_->has_multicast() ? 1u : 0u;
   c.heap_world = static_cast<uint32_t>(heap_->world());
   c.oneshot_max_bytes = cfg_.oneshot_max_bytes;
   c.nvls_ops = cfg_.nvls_ops;
-  c.pad = 0;
+  c.nvls_ctas = static_cast<uint32_t>(cfg_.nvls_ctas);
+  c.stg_bytes = static_cast<uint32_t>(world_.stg_bytes);
+  c.ll_bytes = static_cast<uint32_t>(world_.ll_bytes);
+  c.ll_max_bytes = static_cast<uint32_t>(cfg_.ll_max_bytes);
+  c.ll_oneshot_max = static_cast<uint32_t>(cfg_.ll_oneshot_max);
+  c.tune = cfg_.tune;
   return c;
+}
+
+bool CudaDevice::set_tuning(const std::string &name, long v) {
+  std::lock_guard<std::mutex> lk(m_);
+  if (name == "hybrid_16ths") cfg_.tune.hybrid_16ths = static_cast<uint8_t>(std::max(0l, std::min(15l, v)));
+  else if (name == "nvls_unroll") cfg_.tune.nvls_unroll = static_cast<uint8_t>(v == 4 || v == 16 ? v : 8);
+  else if (name == "reduce_push") cfg_.tune.reduce_push = v ? 1 : 0;
+  else if (name == "bcast_flags") cfg_.tune.bcast_flags = v ? 1 : 0;
+  else if (name == "split_phases") cfg_.tune.split_phases = v ? 1 : 0;
+  else if (name == "nvls_ctas") cfg_.nvls_ctas = static_cast<int>(v);
+  else if (name == "nvls_min_ranks") cfg_.nvls_min_ranks = static_cast<int>(v);
+  else if (name == "max_ctas") cfg_.max_ctas = static_cast<int>(std::max(1l, std::min<long>(MAX_CH - 2, v)));
+  else if (name == "ll_max_bytes") cfg_.ll_max_bytes = static_cast<size_t>(v);
+  else if (name == "ll_oneshot_max") cfg_.ll_oneshot_max = static_cast<size_t>(v);
+  else if (name == "oneshot_max_bytes") cfg_.oneshot_max_bytes = static_cast<size_t>(v);
+  else if (name == "stream_loopback") strm_loopback_ = v != 0;
+  else return false;
+  return true;
+}
+
+long CudaDevice::get_tuning(const std::string &name) const {
+  if (name == "hybrid_16ths") return cfg_.tune.hybrid_16ths;
+  if (name == "nvls_unroll") return cfg_.tune.nvls_unroll;
+  if (name == "reduce_push") return cfg_.tune.reduce_push;
+  if (name == "bcast_flags") return cfg_.tune.bcast_flags;
+  if (name == "split_phases") return cfg_.tune.split_phases;
+  if (name == "nvls_ctas") return cfg_.nvls_ctas;
+  if (name == "nvls_min_ranks") return cfg_.nvls_min_ranks;
+  if (name == "max_ctas") return cfg_.max_ctas;
+  if (name == "ll_max_bytes") return static_cast<long>(cfg_.ll_max_bytes);
+  if (name == "ll_oneshot_max") return static_cast<long>(cfg_.ll_oneshot_max);
+  if (name == "oneshot_max_bytes") return static_cast<long>(cfg_.oneshot_max_bytes);
+  if (name == "stream_loopback") return strm_loopback_ ? 1 : 0;
+  if (name == "stage_bytes") return static_cast<long>(world_.stg_bytes);
+  if (name == "ll_bytes") return static_cast<long>(world_.ll_bytes);
+  return -1;
+}
+
+// ACCL_TUNE="name=value,name=value": experiment without rebuilding (must be identical on every rank)
+void CudaDevice::apply_env_tuning() {
+  const char *e = std::getenv("ACCL_TUNE");
+  if (!e) return;
+  std::string str(e);
+  size_t pos = 0;
+  while (pos < str.size()) {
+    size_t end = str.find(',', pos);
+    if (end == std::string::npos) end = str.size();
+    const std::string kv = str.substr(pos, end - pos);
+    const size_t eq = kv.find('=');
+    if (eq != std::string::npos && !set_tuning(kv.substr(0, eq), std::atol(kv.substr(eq + 1).c_str())))
+      ACCL_ERROR_LOG("ACCL_TUNE: unknown knob '" + kv.substr(0, eq) + "'");
+    pos = end + 1;
+  }
+}
+
+void CudaDevice::drain_locked() {
+  for (auto &r : slot_owner_)
+    if (r && r->status() != operationStatus::COMPLETED) r->wait();
+}
+void CudaDevice::drain() {
+  std::vector<std::shared_ptr<CudaRequest>> pending;
+  {
+    std::lock_guard<std::mutex> lk(m_);
+    for (auto &r : slot_owner_)
+      if (r && r->status() != operationStatus::COMPLETED) pending.push_back(r);
+  }
+  for (auto &r : pending) r->wait();
 }
 
 bool CudaDevice::build_work_item(const Options &o, const CallDesc &d, WorkItem &w, uint32_t &err) {
@@ -458,6 +561,10 @@ ACCLRequest *CudaDevice::start(const Options &options) {
   uint64_t push_bytes = 0, push_src = 0;
   uint32_t push_rank = world_.rank;
   bool put_only = false;
+  // stream id (TDEST) of a streamed result: the tag of stream_put / recv-to-stream when it is a user id
+  const uint32_t res_strm_id = (!strm_loopback_ && options.tag >= STREAM_ID_MIN && options.tag <= STREAM_ID_MAX) ? options.tag : 0;
+  const bool lowered = op0_strm || res_strm;
+  if (lowered && engine_) drain_locked(); // the lowering kernels below are direct launches: they take over the engine's channels
   if (op0_strm || res_strm) {
     const operation sop = options.scenario;
     if (sop != operation::copy && sop != operation::combine && sop != operation::send && sop != operation::recv &&
@@ -471,7 +578,7 @@ ACCLRequest *CudaDevice::start(const Options &options) {
       auto st = allocate(bytes, bufferKind::p2p);
       req->temps.push_back(st);
       strm_bufs[0].reset(new BaseBuffer(st, 0, bytes, options.data_type_io_0));
-      ACCL_CUDART(launch_stream_pop(world_, st->device_addr(), bytes, timeout_us(), s));
+      ACCL_CUDART(launch_stream_pop(world_, st->device_addr(), bytes, 0, timeout_us(), s));
       o.addr_0 = strm_bufs[0].get();
     }
     if (res_strm) {
@@ -517,8 +624,25 @@ ACCLRequest *CudaDevice::start(const Options &options) {
     req->complete(err, 0);
     return h;
   }
+  // ---- CUDA-graph capture: the launch is recorded, nothing executes now — no completion slot, no host-visible
+  // record (a replayed kernel must not write a stale sequence number); the graph's own ordering is the completion
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (s != nullptr && s != cudaStreamLegacy) cudaStreamIsCapturing(s, &cap);
+  if (cap == cudaStreamCaptureStatusActive) {
+    if (push_bytes || engine_ || !req->temps.empty()) {
+      req->immediate = true;
+      req->complete(COLLECTIVE_NOT_IMPLEMENTED, 0); // only plain direct launches on device-resident operands are capturable
+      return h;
+    }
+    w.req_slot = N_REQ_SLOTS - 1; // record reserved for captured launches (replays are stream ordered)
+    w.req_seq = 0;
+    ACCL_CUDART(launch_call(world_, w, nullptr, s));
+    req->immediate = true;
+    req->complete(0, 0);
+    return h;
+  }
   // ---- completion slot
-  const uint32_t slot = next_slot_++ % (N_REQ_SLOTS - 1); // the last record belongs to device-issued calls
+  const uint32_t slot = next_slot_++ % (N_REQ_SLOTS - 1); // the last record belongs to captured launches
   if (slot_owner_[slot]) slot_owner_[slot]->wait(); // ring wrapped: the old occupant must be done
   slot_owner_[slot] = req;
   req->slot = slot;
@@ -534,7 +658,7 @@ ACCLRequest *CudaDevice::start(const Options &options) {
       first.flags |= WF_CHAIN;
       ACCL_CUDART(launch_call(world_, first, &hc_dev_[slot], s));
     }
-    ACCL_CUDART(launch_stream_push(world_, push_rank, push_src, push_bytes, timeout_us(), s));
+    ACCL_CUDART(launch_stream_push(world_, push_rank, push_src, push_bytes, res_strm_id, timeout_us(), s));
     WorkItem tail;
     CallDesc nd = req->desc;
     nd.scenario = static_cast<uint32_t>(operation::nop);
@@ -543,8 +667,15 @@ ACCLRequest *CudaDevice::start(const Options &options) {
     tail.req_slot = slot;
     tail.req_seq = req->seq;
     ACCL_CUDART(launch_call(world_, tail, &hc_dev_[slot], s));
-  } else if (engine_) engine_->submit(w, &hc_dev_[slot], s);
-  else ACCL_CUDART(launch_call(world_, w, &hc_dev_[slot], s));
+  } else if (engine_ && !lowered) {
+    // asynchronous point-to-point calls must not hold the stream: the matching call of the peer may be queued
+    // behind them on ITS stream (send/send then recv/recv); everything else is stream ordered like a launch
+    const bool p2p = options.scenario == operation::send || options.scenario == operation::recv;
+    req->unordered = p2p;
+    engine_->submit(w, &hc_dev_[slot], s, !p2p);
+  } else {
+    ACCL_CUDART(launch_call(world_, w, &hc_dev_[slot], s));
+  }
   req->set_status(operationStatus::EXECUTING);
   return h;
 }

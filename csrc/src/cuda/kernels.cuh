@@ -27,6 +27,8 @@ using namespace accl::dev;
 
 constexpr int BLOCK = 512;
 
+__device__ __forceinline__ uint32_t esize_of(uint32_t dtype) { return dtype_bytes(static_cast<dataType>(dtype)); }
+
 // ------------------------------------------------------------------ context
 struct Ctx {
   const DevWorld &w;
@@ -38,6 +40,11 @@ struct Ctx {
   struct PtrTable *tab; // shared-memory pointer table of this CTA
   __device__ char *heap(uint32_t grank) const { return w.window + static_cast<uint64_t>(grank) * w.heap_bytes; }
   __device__ Ctrl *ctrl(uint32_t grank) const { return reinterpret_cast<Ctrl *>(heap(grank)); }
+  __device__ PadBank &pads() const { return me->pad[it.bank]; }
+  __device__ PadBank &pads_of(uint32_t grank) const { return ctrl(grank)->pad[it.bank]; }
+  __device__ StageBank &stg() const { return me->stg[it.bank]; }
+  __device__ StageBank &stg_of(uint32_t grank) const { return ctrl(grank)->stg[it.bank]; }
+  __device__ uint32_t kind_word() const { return (it.desc.scenario & 0xFFu) | (it.comm_sig << 8); }
   __device__ uint32_t P() const { return it.comm_size; }
   __device__ uint32_t r() const { return it.comm_rank; }
   __device__ uint32_t g(uint32_t comm_rank) const { return it.members[comm_rank]; }
@@ -47,19 +54,6 @@ struct Ctx {
 __device__ __forceinline__ bool wait_ge(const uint32_t *p, uint32_t target, const Ctx &c, uint32_t errbit) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
-#ifdef ACCL_PHASE_TIMING
-  struct WaitTimer {
-    const Ctx &c;
-    unsigned long long t;
-    __device__ explicit WaitTimer(const Ctx &c_) : c(c_), t(c_.cta == 0 ? globaltimer_ns() : 0) {}
-    __device__ ~WaitTimer() {
-      if (c.cta == 0) {
-        atomicAdd(&c.me->dbg_wait_ns, globaltimer_ns() - t);
-        atomicAdd(&c.me->dbg_waits, 1ull);
-      }
-    }
-  } wait_timer(c);
-#endif
   while (static_cast<int32_t>(ld_acquire_sys(p) - target) < 0) {
     ++spins;
     if (spins > 32) nanosleep(spins > 4096 ? 256 : 32);
@@ -82,9 +76,6 @@ __device__ __forceinline__ bool wait_ge(const uint32_t *p, uint32_t target, cons
 __device__ __forceinline__ void chan_sync(const Ctx &c, bool exchange, uint64_t my_off0, uint64_t my_off2,
                                           uint64_t *s_off0, uint64_t *s_off2) {
   __syncthreads(); // every thread's prior writes happen-before the release below
-#ifdef ACCL_PHASE_TIMING
-  const unsigned long long dbg_t0 = (c.cta == 0 && threadIdx.x == 0) ? globaltimer_ns() : 0;
-#endif
   const uint32_t t = threadIdx.x;
   const uint32_t ch = static_cast<uint32_t>(c.cta);
   if (t < c.P()) {
@@ -95,53 +86,50 @@ __device__ __forceinline__ void chan_sync(const Ctx &c, bool exchange, uint64_t 
         s_off2[t] = my_off2;
       }
     } else {
-      Ctrl *pc = c.ctrl(peer);
-      const uint32_t v = c.me->sent[ch][peer] + 1;
-      c.me->sent[ch][peer] = v;
+      PadBank &mine = c.pads();
+      PadBank &theirs = c.pads_of(peer);
+      const uint32_t v = mine.sent[ch][peer] + 1;
+      mine.sent[ch][peer] = v;
       if (exchange) {
-        SyncRec *rr = &pc->rec[ch][c.w.rank];
+        SyncRec *rr = &theirs.rec[ch][c.w.rank];
         st_relaxed_sys(&rr->off0, my_off0);
         st_relaxed_sys(&rr->off2, my_off2);
-        st_relaxed_sys(&rr->kind, c.it.desc.scenario);
+        st_relaxed_sys(&rr->kind, c.kind_word());
       }
-      st_release_sys(&pc->sig[ch][c.w.rank], v);
-      const uint32_t e = c.me->expect[ch][peer] + 1;
-      c.me->expect[ch][peer] = e;
-      if (wait_ge(&c.me->sig[ch][peer], e, c, RECEIVE_TIMEOUT_ERROR) && exchange) {
-        const SyncRec *mr = &c.me->rec[ch][peer];
+      st_release_sys(&theirs.sig[ch][c.w.rank], v);
+      const uint32_t e = mine.expect[ch][peer] + 1;
+      mine.expect[ch][peer] = e;
+      if (wait_ge(&mine.sig[ch][peer], e, c, RECEIVE_TIMEOUT_ERROR) && exchange) {
+        const SyncRec *mr = &mine.rec[ch][peer];
         s_off0[t] = ld_relaxed_sys(&mr->off0);
         s_off2[t] = ld_relaxed_sys(&mr->off2);
-        if (ld_relaxed_sys(&mr->kind) != c.it.desc.scenario) atomicOr(c.err, PACK_SEQ_NUMBER_ERROR);
+        // a peer in a different operation, or in a different communicator that hashes onto this bank
+        if (ld_relaxed_sys(&mr->kind) != c.kind_word()) atomicOr(c.err, PACK_SEQ_NUMBER_ERROR);
       }
     }
   }
   __syncthreads();
-#ifdef ACCL_PHASE_TIMING
-  if (c.cta == 0 && threadIdx.x == 0) {
-    c.me->dbg_sync_ns += globaltimer_ns() - dbg_t0;
-    c.me->dbg_syncs += 1;
-  }
-#endif
 }
 
-// pairwise variant for send/recv: only (me, peer) take part; kinds differ by design
+// pairwise variant for send/recv in direct mode: only (me, peer) take part; kinds differ by design
 __device__ __forceinline__ void pair_sync(const Ctx &c, uint32_t peer_comm_rank, uint64_t my_off, uint32_t my_kind,
                                           uint64_t *peer_off, uint32_t *peer_kind) {
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t ch = static_cast<uint32_t>(c.cta);
     const uint32_t peer = c.g(peer_comm_rank);
-    Ctrl *pc = c.ctrl(peer);
-    const uint32_t v = c.me->sent[ch][peer] + 1;
-    c.me->sent[ch][peer] = v;
-    SyncRec *rr = &pc->rec[ch][c.w.rank];
+    PadBank &mine = c.pads();
+    PadBank &theirs = c.pads_of(peer);
+    const uint32_t v = mine.sent[ch][peer] + 1;
+    mine.sent[ch][peer] = v;
+    SyncRec *rr = &theirs.rec[ch][c.w.rank];
     st_relaxed_sys(&rr->off0, my_off);
     st_relaxed_sys(&rr->kind, my_kind);
-    st_release_sys(&pc->sig[ch][c.w.rank], v);
-    const uint32_t e = c.me->expect[ch][peer] + 1;
-    c.me->expect[ch][peer] = e;
-    if (wait_ge(&c.me->sig[ch][peer], e, c, RECEIVE_TIMEOUT_ERROR)) {
-      const SyncRec *mr = &c.me->rec[ch][peer];
+    st_release_sys(&theirs.sig[ch][c.w.rank], v);
+    const uint32_t e = mine.expect[ch][peer] + 1;
+    mine.expect[ch][peer] = e;
+    if (wait_ge(&mine.sig[ch][peer], e, c, RECEIVE_TIMEOUT_ERROR)) {
+      const SyncRec *mr = &mine.rec[ch][peer];
       *peer_off = ld_relaxed_sys(&mr->off0);
       *peer_kind = ld_relaxed_sys(&mr->kind);
     } else {
@@ -464,12 +452,12 @@ template <NvOp OP> __device__ __forceinline__ Vec16 nv_ld(const void *mc) {
 }
 
 // out[i] = switch-reduce(in[i]) for vectors [v0, v1); out is a multicast
-// address (two-shot allreduce) or a local address (reduce_scatter / reduce)
-template <NvOp OP, bool MC_OUT>
+// address (two-shot allreduce) or a local address (reduce_scatter / reduce).
+// U x 16 B per thread are in flight (in-switch reductions have a long round trip).
+template <NvOp OP, bool MC_OUT, int U>
 __device__ __forceinline__ void nvls_reduce_range(const char *mc_in, char *out, size_t v0, size_t v1, int cta, int nctas) {
   const size_t stride = static_cast<size_t>(nctas) * blockDim.x;
   size_t i = v0 + static_cast<size_t>(cta) * blockDim.x + threadIdx.x;
-  constexpr int U = 8; // in-switch reductions have a long round trip: keep 8 x 16 B per thread in flight
   for (; i + (U - 1) * stride < v1; i += U * stride) {
     Vec16 v[U];
 #pragma unroll
@@ -487,15 +475,23 @@ __device__ __forceinline__ void nvls_reduce_range(const char *mc_in, char *out, 
   }
 }
 
+template <NvOp OP, bool MC_OUT>
+__device__ __forceinline__ void nvls_reduce_unroll(uint32_t unroll, const char *mc_in, char *out, size_t v0, size_t v1, int cta,
+                                                   int nctas) {
+  if (unroll == 4) nvls_reduce_range<OP, MC_OUT, 4>(mc_in, out, v0, v1, cta, nctas);
+  else if (unroll == 16) nvls_reduce_range<OP, MC_OUT, 16>(mc_in, out, v0, v1, cta, nctas);
+  else nvls_reduce_range<OP, MC_OUT, 8>(mc_in, out, v0, v1, cta, nctas);
+}
+
 template <bool MC_OUT>
-__device__ __forceinline__ void nvls_reduce_dispatch(NvOp op, const char *mc_in, char *out, size_t v0, size_t v1, int cta,
-                                                     int nctas) {
+__device__ __noinline__ void nvls_reduce_dispatch(NvOp op, uint32_t unroll, const char *mc_in, char *out, size_t v0, size_t v1, int cta,
+                                                  int nctas) {
   switch (op) {
-  case NvOp::add_f32: nvls_reduce_range<NvOp::add_f32, MC_OUT>(mc_in, out, v0, v1, cta, nctas); break;
-  case NvOp::add_f16: nvls_reduce_range<NvOp::add_f16, MC_OUT>(mc_in, out, v0, v1, cta, nctas); break;
-  case NvOp::add_bf16: nvls_reduce_range<NvOp::add_bf16, MC_OUT>(mc_in, out, v0, v1, cta, nctas); break;
-  case NvOp::max_f16: nvls_reduce_range<NvOp::max_f16, MC_OUT>(mc_in, out, v0, v1, cta, nctas); break;
-  case NvOp::max_bf16: nvls_reduce_range<NvOp::max_bf16, MC_OUT>(mc_in, out, v0, v1, cta, nctas); break;
+  case NvOp::add_f32: nvls_reduce_unroll<NvOp::add_f32, MC_OUT>(unroll, mc_in, out, v0, v1, cta, nctas); break;
+  case NvOp::add_f16: nvls_reduce_unroll<NvOp::add_f16, MC_OUT>(unroll, mc_in, out, v0, v1, cta, nctas); break;
+  case NvOp::add_bf16: nvls_reduce_unroll<NvOp::add_bf16, MC_OUT>(unroll, mc_in, out, v0, v1, cta, nctas); break;
+  case NvOp::max_f16: nvls_reduce_unroll<NvOp::max_f16, MC_OUT>(unroll, mc_in, out, v0, v1, cta, nctas); break;
+  case NvOp::max_bf16: nvls_reduce_unroll<NvOp::max_bf16, MC_OUT>(unroll, mc_in, out, v0, v1, cta, nctas); break;
   default: break;
   }
 }

@@ -208,8 +208,10 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     s_item.comm_size = P;
     s_item.comm_rank = me;
     for (uint32_t r = 0; r < static_cast<uint32_t>(ACCL_MAX_RANKS); ++r) s_item.members[r] = static_cast<uint8_t>(r < P ? r : 0);
-    s_item.desc.scenario = 0x47454D4D; // "GEMM": both ends must be in the same plugin
+    s_item.desc.scenario = 0x47; // 'G': both ends must be in the same plugin
     s_item.timeout_us = p.timeout_us;
+    s_item.bank = 0;
+    s_item.comm_sig = 0x47454Du;
   }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -505,8 +507,10 @@ k_plugin_gemm_rs_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     s_item.comm_size = P;
     s_item.comm_rank = me;
     for (uint32_t r = 0; r < static_cast<uint32_t>(ACCL_MAX_RANKS); ++r) s_item.members[r] = static_cast<uint8_t>(r < P ? r : 0);
-    s_item.desc.scenario = 0x47454D4D;
+    s_item.desc.scenario = 0x47;
     s_item.timeout_us = p.timeout_us;
+    s_item.bank = 0;
+    s_item.comm_sig = 0x47454Du;
   }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");

@@ -32,6 +32,7 @@ CallDesc make_call_desc(const CCLO::Options &o) {
 ACCL::ACCL(std::unique_ptr<CCLO> device, const arithConfigMap &ac) : cclo(std::move(device)), arith_config(ac) {}
 
 ACCL::~ACCL() {
+  alive_->store(false);
   try {
     deinit();
   } catch (...) {

@@ -15,12 +15,41 @@ def plan(op, nbytes, world=8, dtype=F32, esz=4, **kw):
     return A._C.cuda_plan(op, nbytes // esz, dtype, world, **kw)
 
 
+ONE_WAY = ("eager", "ll", "staged")  # protocols without a meeting: slot ring, flag-in-data, payload + flag
+
+
 def test_eager_vs_rendezvous_threshold():
-    assert plan(Op.allreduce, 64 << 10)["algo"] == "eager"            # bytes <= max_eager_size
-    assert plan(Op.allreduce, (64 << 10) + 4)["algo"] != "eager"
+    assert plan(Op.allreduce, 64 << 10)["algo"] in ONE_WAY           # bytes <= max_eager_size
+    assert plan(Op.allreduce, (64 << 10) + 4)["algo"] not in ONE_WAY
     assert plan(Op.allreduce, 64 << 20, compressed=True)["algo"] == "eager"   # compressed calls always use slots
     assert plan(Op.send, 1 << 20)["algo"] == "p2p" and plan(Op.recv, 1 << 20)["algo"] == "p2p"
-    assert plan(Op.send, 1024)["n_ctas"] == 1                         # eager point to point: one channel
+    assert plan(Op.send, 1024)["algo"] == "eager" and plan(Op.send, 1024)["n_ctas"] == 1  # eager point to point: one channel
+
+
+def test_one_way_protocol_selection():
+    # all-reduce: one hop (everybody sends everything) while tiny, reduce-scatter + all-gather above
+    p = plan(Op.allreduce, 1024)
+    assert p["algo"] == "ll" and p["oneshot"] and p["n_ctas"] == 1
+    p = plan(Op.allreduce, 64 << 10)
+    assert p["algo"] == "ll" and not p["oneshot"]                     # shards of 8 KiB <= ll_max_bytes
+    p = plan(Op.allreduce, 2 << 20, max_eager_bytes=4 << 20)
+    assert p["algo"] == "staged" and not p["oneshot"]                 # shards of 256 KiB: payload + release flag
+    # sizes that do not split into 16-byte shards go one-shot while small, to the slot ring otherwise
+    assert plan(Op.allreduce, 20000)["oneshot"]
+    assert plan(Op.allreduce, (1 << 20) + 4, max_eager_bytes=4 << 20)["algo"] == "eager"
+    # per-peer message decides for the others
+    assert plan(Op.allgather, 8 << 10)["algo"] == "ll"
+    assert plan(Op.allgather, 256 << 10, max_eager_bytes=1 << 20)["algo"] == "staged"
+    assert plan(Op.reduce_scatter, 16 << 10)["algo"] == "ll"
+    assert plan(Op.bcast, 32 << 10)["algo"] == "staged"
+    # a message that does not fit the staging region falls back to the slot ring
+    assert plan(Op.allgather, 2 << 20, max_eager_bytes=4 << 20)["algo"] == "eager"
+    assert plan(Op.allgather, 2 << 20, max_eager_bytes=4 << 20, stage_kb=4096)["algo"] == "staged"
+    # no staging configured: everything one-way is the slot ring
+    assert plan(Op.allreduce, 1024, stage_kb=0, ll_kb=0)["algo"] == "eager"
+    # channel counts: every channel owns 1/32 of a region
+    assert plan(Op.allgather, 256 << 10, max_eager_bytes=1 << 20)["n_ctas"] == 8   # 32 KiB per channel
+    assert plan(Op.allgather, 1 << 20, max_eager_bytes=1 << 20)["n_ctas"] == 32
 
 
 def test_allreduce_algorithm_by_size_and_world():
@@ -28,6 +57,7 @@ def test_allreduce_algorithm_by_size_and_world():
     assert plan(Op.allreduce, 128 << 10, world=8)["algo"] == "p2p_oneshot"
     assert plan(Op.allreduce, 512 << 10, world=8)["algo"] == "nvls"
     assert plan(Op.allreduce, 512 << 10, world=2)["algo"] == "p2p_oneshot"
+    assert plan(Op.allreduce, 128 << 10, world=8, max_eager_bytes=1 << 20)["algo"] in ONE_WAY
     assert plan(Op.allreduce, 4 << 20, world=2)["algo"] == "p2p"
     assert plan(Op.allreduce, 4 << 20, world=8, has_mc=False)["algo"] == "p2p"
     assert plan(Op.allreduce, 4 << 20, world=4, nvls_min_ranks=99)["algo"] == "p2p"
@@ -42,12 +72,12 @@ def test_nvls_only_for_ops_that_win_through_the_switch():
 
 def test_channel_counts():
     assert plan(Op.allreduce, 256 << 20, max_ctas=128)["n_ctas"] == 64      # measured: 64 beats 128 through the switch
-    assert plan(Op.allreduce, 64 << 20, world=2, max_ctas=128)["n_ctas"] == 64
+    assert plan(Op.allreduce, 64 << 20, world=2, max_ctas=128)["n_ctas"] == 128    # peer loads / stores want them all
     assert plan(Op.allreduce, 256 << 20, world=2, max_ctas=128)["n_ctas"] == 128
     assert plan(Op.reduce_scatter, 32 << 20, max_ctas=128)["n_ctas"] == 128  # 8 x 32 MiB moved: all channels
     assert plan(Op.allgather, 128 << 10, max_ctas=128)["n_ctas"] == 8        # 8 x 128 KiB moved at 128 KiB per channel
     assert plan(Op.allreduce, 1024, max_ctas=128)["n_ctas"] == 1
-    assert plan(Op.allreduce, 64 << 10, max_ctas=128)["n_ctas"] == 4         # eager: 16 KiB per channel, <= 16 channels
-    assert plan(Op.allreduce, 256 << 20, max_ctas=1000)["n_ctas"] <= 160     # never more channels than sync pads
+    assert plan(Op.allreduce, 64 << 10, max_ctas=128, stage_kb=0, ll_kb=0)["n_ctas"] == 4   # slot ring: 16 KiB per channel, <= 16 channels
+    assert plan(Op.allreduce, 256 << 20, max_ctas=1000, nvls_min_ranks=99)["n_ctas"] <= 128   # never more channels than sync pads
     assert plan(Op.copy, 1 << 30)["algo"] == "local" and plan(Op.copy, 1 << 30)["n_ctas"] == 296
     assert plan(Op.barrier, 0)["n_ctas"] == 1 and plan(Op.nop, 0)["algo"] == "local"
