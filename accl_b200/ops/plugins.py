@@ -21,11 +21,15 @@ def _stream_handle(accl):
     return h if h else 1  # cudaStreamLegacy
 
 
-def gemm_reduce_scatter(accl: Accl, a: torch.Tensor, w: torch.Tensor, out: Buffer = None) -> Buffer:
-    """out[M/P, N] (bf16, in the symmetric heap) = reduce_scatter over ranks of a[M, K_r] @ w[N, K_r]^T.
+def gemm_reduce_scatter(accl: Accl, a: torch.Tensor, w: torch.Tensor, out: Buffer = None, variant: int = 0,
+                        out_dtype=torch.bfloat16) -> Buffer:
+    """out[M/P, N] (in the symmetric heap) = reduce_scatter over ranks of a[M, K_r] @ w[N, K_r]^T.
 
     `a` and `w` are this rank's K-slices (bf16, contiguous, on this rank's GPU).
     Needs M % (128 * world) == 0, N % 256 == 0, K_r % 64 == 0.  Stream ordered.
+    The shard is bf16 (partials added in bf16 by the TMA unit) or, with an fp32 `out` buffer / out_dtype, fp32
+    (the P partial products are accumulated without intermediate rounding).  variant: 0 automatic, 1 one CTA per
+    128 x 256 tile, 2 CTA pair (tcgen05 cta_group::2) per 256 x 256 tile (needs M % (256 * world) == 0).
     """
     assert a.is_cuda and w.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.is_contiguous() and w.is_contiguous() and a.shape[1] == w.shape[1]
@@ -33,9 +37,9 @@ def gemm_reduce_scatter(accl: Accl, a: torch.Tensor, w: torch.Tensor, out: Buffe
     N = w.shape[0]
     P = accl.world
     if out is None:
-        out = accl.create_buffer(M // P * N, torch.bfloat16)
+        out = accl.create_buffer(M // P * N, out_dtype)
     assert out.length >= M // P * N
-    _C.gemm_reduce_scatter(accl.impl, a.data_ptr(), w.data_ptr(), out.impl, M, N, K, _stream_handle(accl))
+    _C.gemm_reduce_scatter(accl.impl, a.data_ptr(), w.data_ptr(), out.impl, M, N, K, _stream_handle(accl), variant)
     return out
 
 

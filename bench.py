@@ -85,6 +85,7 @@ def main():
     ap.add_argument("--dtype", default="float32")
     ap.add_argument("--max-ctas", type=int, default=int(os.environ.get("ACCL_MAX_CTAS", 128)))
     ap.add_argument("--engine", action="store_true", help="route calls through the persistent engine kernel")
+    ap.add_argument("--tune", default="", help="name=value,... runtime knobs (Accl.set_tuning), identical on every rank")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-nccl", action="store_true")
     args = ap.parse_args()
@@ -158,45 +159,84 @@ def main():
         heap_mb = max(512, (4 * nbytes >> 20) + 256)
         acc = A.cuda_rank(rank, world, local, heap_mb=heap_mb, max_ctas=args.max_ctas, engine=args.engine)
         acc.initialize(n_egr_rx_bufs=4, egr_rx_buf_size=64 << 10, max_egr_size=64 << 10, max_rndzv_size=1 << 30)
+        for kv in filter(None, args.tune.split(",")):
+            k, v = kv.split("=")
+            acc.set_tuning(k, int(v))
         src = acc.create_buffer(n, dt)
         dst = acc.create_buffer(n, dt)
-        src.dev.fill_(1.0)
+        # rank-dependent pseudo-random operands; the guard below compares the WHOLE result with a float64 reference
+        g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+        src.dev.copy_((torch.rand(n, device="cuda", generator=g) * 2 - 1).to(dt))
         dst.dev.zero_()
 
         def fn():
             acc.allreduce(src, dst, n, A.SUM, from_fpga=True, to_fpga=True, run_async=True).free()
 
-        # correctness guard: a wrong answer must not produce a number
+        # correctness guard: a wrong (mis-sharded, permuted, partially reduced) answer must not produce a number
         fn()
         torch.cuda.synchronize()
-        got = dst.dev[: 1024].float().cpu()
-        assert torch.allclose(got, torch.full_like(got, float(world))), f"allreduce wrong: {got[:4]} != {world}"
+        chunk = 32 << 20
+        worst = 0.0
+        for o in range(0, n, chunk):
+            ref = src.dev[o:o + chunk].double()
+            if use_dist:
+                dist.all_reduce(ref)
+            worst = max(worst, float((dst.dev[o:o + chunk].double() - ref).abs().max()))
+            del ref
+        tol = {torch.float32: 1e-5, torch.float16: 2e-2, torch.bfloat16: 1e-1}.get(dt, 1e-5) * max(world, 1)
+        assert worst <= tol, f"allreduce wrong: max abs error {worst} > {tol}"
+        result["max_abs_err_vs_fp64_ref"] = worst
         if sampler:
             sampler.start()
         ms = timed(fn, K, W)
-        launches = K  # one engine kernel (k_call) per all-reduce; nothing else runs in the timed region
+        # kernels of this library launched inside the timed region: one k_call per all-reduce (direct launch), or one
+        # k_submit proxy per all-reduce handing the command to the resident k_engine kernel (engine mode)
+        launches = K
         impl_name = "accl_b200"
         e2e = None
+        nccl = None
+        if use_dist and not args.no_nccl:
+            x = src.dev.clone() if nbytes <= (1 << 30) else torch.ones(n, dtype=dt, device="cuda")
+            ms_n = timed(lambda: dist.all_reduce(x), max(3, K // 2), 3)
+            nccl = {"ms_per_step": ms_n, "busbw_GBps": nbytes / ms_n * 1e-6 * busbw_factor(world)}
+            del x
         if not args.no_e2e:
             # public API, host-resident operands: pinned H2D of the input and D2H of the result every step
-            src.host.fill_(1.0)
+            src.host.copy_(torch.rand(n, generator=torch.Generator().manual_seed(99 + rank)).to(dt))
 
             def fn_e2e():
                 acc.allreduce(src, dst, n, A.SUM)  # from_fpga=False, to_fpga=False, blocking
 
             e_steps = max(3, min(K, 10))
             ms_e = timed(fn_e2e, e_steps, 3)
-            assert float(dst.host[0]) == float(world)
+            # the value that came back must be the sum of what went in (first / last elements against a float64 reference)
+            probe = torch.cat([src.host[:1024], src.host[-1024:]]).double().cuda()
+            if use_dist:
+                dist.all_reduce(probe)
+            got = torch.cat([dst.host[:1024], dst.host[-1024:]]).double().cuda()
+            assert float((got - probe).abs().max()) <= tol, "e2e allreduce wrong"
             e2e = {"value": nbytes / ms_e * 1e-6 * busbw_factor(world), "unit": "GB/s", "ms_per_step": ms_e,
                    "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": e_steps,
                    "note": "accl allreduce(sendbuf, recvbuf) with host-resident data: sync_to_device + collective + sync_from_device"}
-        nccl = None
-        if use_dist and not args.no_nccl:
-            x = torch.ones(n, dtype=dt, device="cuda")
-            ms_n = timed(lambda: dist.all_reduce(x), max(3, K // 2), 3)
-            nccl = {"ms_per_step": ms_n, "busbw_GBps": nbytes / ms_n * 1e-6 * busbw_factor(world)}
+            if use_dist and not args.no_nccl:
+                # the same end-to-end step on NCCL: pinned H2D, dist.all_reduce, D2H, blocking
+                hx = torch.empty(n, dtype=dt).pin_memory()
+                hy = torch.empty(n, dtype=dt).pin_memory()
+                hx.copy_(src.host)
+                dx = torch.empty(n, dtype=dt, device="cuda")
+
+                def nccl_e2e():
+                    dx.copy_(hx, non_blocking=True)
+                    dist.all_reduce(dx)
+                    hy.copy_(dx, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+
+                ms_ne = timed(nccl_e2e, e_steps, 3)
+                e2e["nccl_e2e"] = {"value": nbytes / ms_ne * 1e-6 * busbw_factor(world), "ms_per_step": ms_ne}
+                del hx, hy, dx
         result["nccl_same_run"] = nccl
         result["backend"] = acc.describe()
+        result["mode"] = "engine" if args.engine else "direct"
     clocks = sampler.stop() if sampler else None
     algbw = nbytes / ms * 1e-6
     value = algbw * busbw_factor(world)
@@ -212,6 +252,10 @@ def main():
                        "roofline_GBps_per_dir": 900, "timer": "CUDA events, max over ranks"},
             "algbw_GBps": algbw, "gpu_launches": launches, "clocks": clocks,
         }
+        if world > 1:
+            # bytes per direction per GPU: in-switch two-shot moves M (1 + 1/P), peer two-shot 2 M (P-1)/P
+            out["link_GBps_per_dir_nvls_accounting"] = nbytes * (1 + 1.0 / world) / ms * 1e-6
+            out["frac_of_900_GBps_link"] = out["link_GBps_per_dir_nvls_accounting"] / 900.0
         if e2e is not None:
             out["e2e"] = e2e
         out.update(result)

@@ -24,9 +24,12 @@ def main():
     ap.add_argument("--sizes", default="1024,16384,65536,262144,1048576,4194304")
     ap.add_argument("--modes", default="direct,engine")
     ap.add_argument("--max-ctas", type=int, default=64)
-    ap.add_argument("--egr-kb", type=int, default=64)
+    ap.add_argument("--egr-kb", type=int, default=64, help="eager threshold (one-way protocols up to it)")
+    ap.add_argument("--slot-kb", type=int, default=64, help="eager slot size")
     ap.add_argument("--nvls-min-ranks", type=int, default=3)
     ap.add_argument("--big-mb", type=int, default=0, help="also time one all-reduce of this size (MiB)")
+    ap.add_argument("--graph", action="store_true", help="also time CUDA-graph replays (direct mode and NCCL)")
+    ap.add_argument("--engine-workers", type=int, default=32)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -35,6 +38,33 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sizes = [int(s) for s in args.sizes.split(",")]
     maxb = max(max(sizes), args.big_mb << 20)
+
+    def graph_time(fn, per_graph=20, replays=6):
+        """us per call when `per_graph` calls are captured once and replayed (launch-bound loops belong in a graph)"""
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            fn()
+            st.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                for _ in range(per_graph):
+                    fn()
+            g.replay()
+            st.synchronize()
+            if world > 1:
+                dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            for _ in range(replays):
+                g.replay()
+            b.record(st)
+            st.synchronize()
+        ms = a.elapsed_time(b) / (replays * per_graph)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms * 1e3
 
     def ev_time(fn, iters):
         for _ in range(5):
@@ -57,11 +87,24 @@ def main():
         return ms * 1e3
 
     rows = []
+    fh = None
+    if rank == 0 and args.out:
+        os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+        fh = open(args.out, "w")
+
+    def emit(row):
+        rows.append(row)
+        if rank == 0:
+            print(json.dumps(row), flush=True)
+            if fh:
+                fh.write(json.dumps(row) + "\n")
+                fh.flush()
+
     port = int(os.environ.get("MASTER_PORT", 29500)) + 137
     for mi, mode in enumerate(args.modes.split(",")):
         acc = A.cuda_rank(rank, world, local, port=port + 11 * mi, heap_mb=(3 * maxb >> 20) + 256, max_ctas=args.max_ctas,
-                          engine=(mode == "engine"), nvls_min_ranks=args.nvls_min_ranks)
-        acc.initialize(n_egr_rx_bufs=4, egr_rx_buf_size=args.egr_kb << 10, max_egr_size=args.egr_kb << 10, max_rndzv_size=1 << 30)
+                          engine=(mode == "engine"), nvls_min_ranks=args.nvls_min_ranks, engine_workers=args.engine_workers)
+        acc.initialize(n_egr_rx_bufs=4, egr_rx_buf_size=args.slot_kb << 10, max_egr_size=max(args.egr_kb, args.slot_kb) << 10, max_rndzv_size=1 << 30)
         if rank == 0:
             print("#", acc.describe(), flush=True)
         n_max = maxb // 4
@@ -101,11 +144,13 @@ def main():
                     r.free()
                 row = dict(mode=mode, op=op, bytes=nbytes, world=world, us_event_async=round(us_async, 2),
                            us_device_median=round(statistics.median(durs), 2), us_device_min=round(min(durs), 2))
+                if args.graph and mode == "direct" and op != "nop":
+                    row["us_graph"] = round(graph_time(lambda: call(run_async=True).free()), 2)
                 if ref is not None and world > 1 and mi == 0:
                     row["us_nccl"] = round(ev_time(ref, iters), 2)
-                rows.append(row)
-                if rank == 0:
-                    print(json.dumps(row), flush=True)
+                    if args.graph:
+                        row["us_nccl_graph"] = round(graph_time(ref), 2)
+                emit(row)
         if args.big_mb:
             n = (args.big_mb << 20) // 4
             us = ev_time(lambda: acc.allreduce(s, d, n, A.SUM, run_async=True, **kw).free(), 10)
@@ -115,19 +160,14 @@ def main():
             if world > 1 and mi == 0:
                 un = ev_time(lambda: dist.all_reduce(nx[:n]), 10)
                 row.update(us_nccl=round(un, 1), nccl_busbw=round((args.big_mb << 20) / un * 1e-3 * f, 1))
-            rows.append(row)
-            if rank == 0:
-                print(json.dumps(row), flush=True)
+            emit(row)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         del s, d
         acc.deinit()
-    if rank == 0 and args.out:
-        os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
-        with open(args.out, "w") as fh:
-            for r in rows:
-                fh.write(json.dumps(r) + "\n")
+    if fh:
+        fh.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

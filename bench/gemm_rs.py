@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--gk", dest="k", type=int, default=8192)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 single CTA per tile, 2 CTA pair (cta_group::2)")
+    ap.add_argument("--f32", action="store_true", help="fp32 output shard (fp32 accumulation of the partial products)")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -39,7 +41,7 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(7 + rank)
     x = (torch.randn(M, K, device="cuda", generator=g) * 0.25).bfloat16()
     w = (torch.randn(N, K, device="cuda", generator=g) * 0.25).bfloat16()
-    out = acc.create_buffer(M // world * N, torch.bfloat16)
+    out = acc.create_buffer(M // world * N, torch.float32 if a.f32 else torch.bfloat16)
     ref_out = torch.empty(M // world, N, dtype=torch.bfloat16, device="cuda")
 
     def timed(fn, iters):
@@ -63,7 +65,7 @@ def main():
         return ms
 
     def fused():
-        gemm_reduce_scatter(acc, x, w, out)
+        gemm_reduce_scatter(acc, x, w, out, variant=a.variant)
 
     def baseline():
         c = x @ w.t()
@@ -86,18 +88,35 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
     nvlink_bytes = M * N * 2 * (world - 1) / world  # partial tiles leaving this GPU
-    t_roof = max(flops / (peak_tf * 1e12), nvlink_bytes / 770e9) * 1e3
+    if a.f32:
+        nvlink_bytes *= 2
+    link = 900e9  # nominal NVLink 5 per direction (BASELINE.json); the measured peer-copy rate is ~680-770 GB/s
+    t_roof = max(flops / (peak_tf * 1e12), nvlink_bytes / link) * 1e3
     err = None
+    err32 = None
     if a.check:
         fused()
         baseline()
         torch.cuda.synchronize()
-        err = float((out.dev.view(M // world, N).float() - ref_out.float()).abs().max())
+        got = out.dev.view(M // world, N).float()
+        err = float((got - ref_out.float()).abs().max())
+        # against an fp32 reference of the same op: fp32 matmul of the bf16 operands, summed over ranks in fp32
+        rows = slice(rank * (M // world), (rank + 1) * (M // world))
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        full = x.float() @ w.float().t()
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        if world > 1:
+            dist.all_reduce(full)
+        err32 = float((got - full[rows]).abs().max())
+        ref32 = float((ref_out.float() - full[rows]).abs().max())
     if rank == 0:
         row = dict(op="gemm_reduce_scatter", m=M, n=N, k_per_rank=K, world=world, fused_ms=ms_f, cublas_nccl_ms=ms_b,
                    cublas_gemm_only_ms=ms_g, fused_tflops=flops / ms_f * 1e-9, cublas_tflops=flops / ms_g * 1e-9,
                    speedup_vs_cublas_nccl=ms_b / ms_f, roofline_ms=t_roof, frac_of_roofline=t_roof / ms_f,
-                   peak_source="MEASURED_PEAKS.json bf16_tflops" if peaks else "fallback 1590", max_abs_err=err)
+                   peak_source="MEASURED_PEAKS.json bf16_tflops" if peaks else "fallback 1590", link_GBps=900,
+                   variant=a.variant, out_dtype="fp32" if a.f32 else "bf16", max_abs_err_vs_cublas_nccl=err,
+                   max_abs_err_vs_fp32_ref=err32, cublas_nccl_err_vs_fp32_ref=ref32 if a.check else None)
         print(json.dumps(row), flush=True)
         if a.out:
             os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)

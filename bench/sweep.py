@@ -37,7 +37,12 @@ def main():
     ap.add_argument("--step", type=int, default=2)
     ap.add_argument("--dtype", default="float32")
     ap.add_argument("--max-ctas", type=int, default=128)
-    ap.add_argument("--egr-kb", type=int, default=64, help="eager threshold / slot size in KiB")
+    ap.add_argument("--egr-kb", type=int, default=4096, help="eager threshold in KiB: messages up to it use the one-way protocols")
+    ap.add_argument("--slot-kb", type=int, default=64, help="eager slot (RX buffer) size in KiB")
+    ap.add_argument("--batches", type=int, default=5, help="device-timed batches per point; the median is reported")
+    ap.add_argument("--graph", action="store_true", help="add CUDA-graph replay columns (ours in direct mode, and NCCL)")
+    ap.add_argument("--tune", default="", help="name=value,... runtime knobs, identical on every rank")
+    ap.add_argument("--engine-workers", type=int, default=0)
     ap.add_argument("--oneshot-kb", type=int, default=2048)
     ap.add_argument("--nvls-min-ranks", type=int, default=3)
     ap.add_argument("--engine", action="store_true")
@@ -51,9 +56,13 @@ def main():
     dt = getattr(torch, args.dtype)
     esz = torch.empty((), dtype=dt).element_size()
     max_bytes = 1 << args.max_log2
-    acc = A.cuda_rank(rank, world, local, heap_mb=(3 * max_bytes >> 20) + 512, max_ctas=args.max_ctas, engine=args.engine,
-                      oneshot_kb=args.oneshot_kb, nvls_min_ranks=args.nvls_min_ranks)
-    acc.initialize(n_egr_rx_bufs=4, egr_rx_buf_size=args.egr_kb << 10, max_egr_size=args.egr_kb << 10, max_rndzv_size=1 << 30)
+    acc = A.cuda_rank(rank, world, local, heap_mb=(3 * max_bytes >> 20) + 768, max_ctas=args.max_ctas, engine=args.engine,
+                      oneshot_kb=args.oneshot_kb, nvls_min_ranks=args.nvls_min_ranks, engine_workers=args.engine_workers)
+    acc.initialize(n_egr_rx_bufs=4, egr_rx_buf_size=args.slot_kb << 10, max_egr_size=max(args.egr_kb, args.slot_kb) << 10,
+                   max_rndzv_size=1 << 30)
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        acc.set_tuning(k, int(v))
     if rank == 0:
         print("#", acc.describe(), flush=True)
     big_s = acc.create_buffer(max_bytes // esz, dt)
@@ -62,9 +71,10 @@ def main():
     nx = torch.ones(max_bytes // esz, dtype=dt, device="cuda") if not args.no_nccl and world > 1 else None
     ny = torch.empty(max_bytes // esz, dtype=dt, device="cuda") if nx is not None else None
 
-    def timed(fn, iters, batches=3):
+    def timed(fn, iters, batches=None):
         """Median over `batches` device-timed batches (max over ranks each): a shared box shows
         occasional multi-ms hiccups, for NCCL and for us alike; the median keeps one from deciding a row."""
+        batches = batches or args.batches
         for _ in range(3):
             fn()
         per_batch = max(2, iters // batches)
@@ -88,57 +98,113 @@ def main():
             out.append(ms)
         return sorted(out)[len(out) // 2]
 
+    def device_us(call, reps=15):
+        """engine-measured duration of the call itself (completion record: first CTA in -> last CTA out, or
+        fetched -> retired in engine mode) — the reference's PERFCNT / get_duration; median, max over ranks"""
+        durs = []
+        for _ in range(reps):
+            if world > 1:
+                dist.barrier()
+            r = call()
+            r.wait()
+            durs.append(r.duration_ns() * 1e-3)
+            r.free()
+        us = sorted(durs)[len(durs) // 2]
+        if world > 1:
+            t = torch.tensor([us], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            us = float(t.item())
+        return us
+
+    def graph_us(fn, per_graph=20, replays=5):
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            fn()
+            st.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                for _ in range(per_graph):
+                    fn()
+            g.replay()
+            st.synchronize()
+            if world > 1:
+                dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            for _ in range(replays):
+                g.replay()
+            b.record(st)
+            st.synchronize()
+        ms = a.elapsed_time(b) / (replays * per_graph)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms * 1e3
+
     rows = []
     for op in args.ops.split(","):
         for lg in range(args.min_log2, args.max_log2 + 1, args.step):
             nbytes = 1 << lg
             n = nbytes // esz          # message size in the NCCL-tests sense (total for AG/RS)
             per = n // world           # per-rank block for AG / RS / scatter / gather
-            iters = 150 if nbytes <= (1 << 20) else (30 if nbytes <= (1 << 26) else 9)
+            iters = 200 if nbytes <= (1 << 20) else (50 if nbytes <= (1 << 26) else 15)
             kw = dict(from_fpga=True, to_fpga=True, run_async=True)
             s, d = big_s, big_d
             if op == "allreduce":
-                f = lambda: acc.allreduce(s, d, n, A.SUM, **kw).free()
+                c = lambda: acc.allreduce(s, d, n, A.SUM, **kw)
                 g = (lambda: dist.all_reduce(nx[:n])) if nx is not None else None
             elif op == "allgather":
                 if per == 0: continue
-                f = lambda: acc.allgather(s, d, per, **kw).free()
+                c = lambda: acc.allgather(s, d, per, **kw)
                 g = (lambda: dist.all_gather_into_tensor(ny[:per * world], nx[:per])) if nx is not None else None
             elif op == "reduce_scatter":
                 if per == 0: continue
-                f = lambda: acc.reduce_scatter(s, d, per, A.SUM, **kw).free()
+                c = lambda: acc.reduce_scatter(s, d, per, A.SUM, **kw)
                 g = (lambda: dist.reduce_scatter_tensor(ny[:per], nx[:per * world])) if nx is not None else None
             elif op == "bcast":
-                f = lambda: acc.bcast(s, n, 0, **kw).free()
+                c = lambda: acc.bcast(s, n, 0, **kw)
                 g = (lambda: dist.broadcast(nx[:n], 0)) if nx is not None else None
             elif op == "reduce":
-                f = lambda: acc.reduce(s, d, n, 0, A.SUM, **kw).free()
+                c = lambda: acc.reduce(s, d, n, 0, A.SUM, **kw)
                 g = (lambda: dist.reduce(nx[:n], 0)) if nx is not None else None
             elif op == "scatter":
                 if per == 0: continue
-                f = lambda: acc.scatter(s, d, per, 0, **kw).free()
+                c = lambda: acc.scatter(s, d, per, 0, **kw)
                 sl = [nx[i * per:(i + 1) * per] for i in range(world)] if nx is not None and rank == 0 else None
                 g = (lambda: dist.scatter(ny[:per], sl, src=0)) if nx is not None else None
             elif op == "gather":
                 if per == 0: continue
-                f = lambda: acc.gather(s, d, per, 0, **kw).free()
+                c = lambda: acc.gather(s, d, per, 0, **kw)
                 gl = [ny[i * per:(i + 1) * per] for i in range(world)] if nx is not None and rank == 0 else None
                 g = (lambda: dist.gather(nx[:per], gl, dst=0)) if nx is not None else None
             elif op == "alltoall":
                 if per == 0: continue
-                f = lambda: acc.alltoall(s, d, per, **kw).free()
+                c = lambda: acc.alltoall(s, d, per, **kw)
                 g = (lambda: dist.all_to_all_single(ny[:per * world], nx[:per * world])) if nx is not None else None
             else:
                 continue
+            f = lambda: c().free()  # noqa: E731
             ms = timed(f, iters)
-            row = dict(op=op, bytes=nbytes, dtype=args.dtype, world=world, accl_us=ms * 1e3,
-                       accl_busbw=nbytes / ms * 1e-6 * factor(op, world))
+            row = dict(op=op, bytes=nbytes, dtype=args.dtype, world=world, mode="engine" if args.engine else "direct",
+                       accl_us=ms * 1e3, accl_busbw=nbytes / ms * 1e-6 * factor(op, world),
+                       accl_device_us=device_us(c) if nbytes <= (64 << 20) else None)
+            if args.graph and not args.engine and nbytes <= (4 << 20):
+                row["accl_graph_us"] = graph_us(f)
             if g is not None:
                 ms_n = timed(g, iters)
                 row.update(nccl_us=ms_n * 1e3, nccl_busbw=nbytes / ms_n * 1e-6 * factor(op, world), speedup=ms_n / ms)
+                if args.graph and nbytes <= (4 << 20):
+                    row["nccl_graph_us"] = graph_us(g)
+                    if "accl_graph_us" in row:
+                        row["speedup_graph"] = row["nccl_graph_us"] / row["accl_graph_us"]
             rows.append(row)
             if rank == 0:
                 print(json.dumps(row), flush=True)
+                if args.out:  # survive a timeout: every row is on disk as soon as it is measured
+                    os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+                    with open(args.out + ".jsonl", "a") as jf:
+                        jf.write(json.dumps(row) + "\n")
     if rank == 0 and args.out and rows:
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
         keys = sorted({k for r in rows for k in r}, key=lambda k: (k not in ("op", "bytes"), k))

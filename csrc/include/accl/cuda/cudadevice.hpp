@@ -48,8 +48,10 @@ struct CudaConfig {
   int nvls_ctas = 64;          // channel cap of the NVLS two-shot all-reduce
   size_t stage_bytes = 0;      // staging region per (bank, parity, source) of ALGO_STAGED (0: sized from the heap)
   size_t ll_bytes = 0;         // same for ALGO_LL
-  size_t ll_max_bytes = 16u << 10;   // per-peer message size up to which the flag-in-data protocol is used
+  size_t ll_max_bytes = 1u << 20;    // per-peer message size up to which the flag-in-data protocol is used (if it fits)
+  size_t staged_max_bytes = 0;       // per-peer messages that do not fit LL use ALGO_STAGED up to this size (0: never)
   size_t ll_oneshot_max = 32u << 10; // all-reduce: one hop (everybody sends everything) up to this size
+  size_t wire_min_bytes = 256u << 10; // compressed-wire collectives from this size on use the fused two-shot
   Tune tune{0, 8, 0, 0, 0, {0, 0, 0}};
 };
 

@@ -47,7 +47,8 @@ enum Algo : uint32_t {
   ALGO_P2P = 4,          // peer loads/stores on the mapped heaps (one-shot or two-shot by op)
   ALGO_P2P_ONESHOT = 5,  // every rank pulls everything (small allreduce without slots)
   ALGO_LL = 6,           // staged one-way exchange, flag carried inside every 8 data bytes (no fence, one hop)
-  ALGO_STAGED = 7        // staged one-way exchange, payload then release-flag; consumer copies / reduces out of staging
+  ALGO_STAGED = 7,       // staged one-way exchange, payload then release-flag; consumer copies / reduces out of staging
+  ALGO_WIRE = 8          // wire-compressed two-shot over the scratch area: cast fused into the NVLink stores / loads (compress.cuh)
 };
 
 struct SyncRec { // rendezvous "address exchange" record, written by a peer next to its signal
@@ -128,7 +129,7 @@ struct Ctrl {
   // ---- completion records (direct launches)
   Completion comp[N_REQ_SLOTS];
   // ---- persistent engine (engine.cu): configuration, command ring, doorbells
-  uint32_t plan_cfg_words[16];    // PlanCfg image (plan.hpp) for device-side planning
+  uint32_t plan_cfg_words[24];    // PlanCfg image (plan.hpp) for device-side planning
   uint32_t engine_timeout_us;
   uint32_t engine_exit;           // workers leave when set
   unsigned long long cmd_tail;    // producers (host proxies, plugin kernels) take tickets here

@@ -31,6 +31,12 @@ struct PlanCfg {
   uint32_t ll_bytes;       // same for ALGO_LL
   uint32_t ll_max_bytes;   // per-peer message size up to which the flag-in-data protocol is used
   uint32_t ll_oneshot_max; // all-reduce: everybody-sends-everything (one hop) up to this size, two hops above
+  uint32_t wire_min_bytes; // compressed-wire calls at least this big use the fused two-shot (0: always the slot ring)
+  uint32_t staged_max_bytes; // per-peer messages up to this size that do not fit the LL protocol use ALGO_STAGED
+                             // (0: they go to the slot ring / rendezvous instead: measured faster from ~1 MiB on)
+  uint32_t engine_mode;    // calls run inside the persistent engine: prefer ONE channel when the message fits it
+                           // (the control CTA executes it inline, no hand-over to the workers)
+  uint32_t pad;
   Tune tune;
 };
 constexpr uint32_t NVLS_OPS_DEFAULT = (1u << static_cast<uint32_t>(operation::allreduce)) |
@@ -47,6 +53,7 @@ ACCL_HD uint32_t plan_ctas(uint64_t bytes, uint64_t per_cta, uint32_t cap) {
 // One-way staged protocols (staged.cuh): does a per-peer message of `m` bytes fit, and on how many channels?
 // Every channel owns a fixed 1 / STG_CH slice of the staging region.  Returns 0 when it does not fit.
 ACCL_HD uint32_t plan_staged_ctas(uint64_t m, bool ll, const PlanCfg &cfg, uint32_t cap) {
+  if (!ll && m > cfg.staged_max_bytes) return 0;
   const uint64_t region = ll ? cfg.ll_bytes : cfg.stg_bytes;
   const uint64_t slice = (region / static_cast<uint64_t>(STG_CH)) & ~127ull;
   if (!slice) return 0;
@@ -58,6 +65,7 @@ ACCL_HD uint32_t plan_staged_ctas(uint64_t m, bool ll, const PlanCfg &cfg, uint3
   const uint64_t lim = cap < static_cast<uint32_t>(STG_CH) ? cap : static_cast<uint32_t>(STG_CH);
   if (need < 1) need = 1;
   if (need > lim) return 0;
+  if (cfg.engine_mode && need == 1 && units <= 2048) want = 1;
   if (want < need) want = need;
   if (want > lim) want = lim;
   // parts are ceil(units / n): re-check capacity for the chosen n
@@ -119,6 +127,20 @@ ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
         w.n_ctas = n;
         return;
       }
+    }
+  }
+  // compressed wire, uncompressed operands, large message: the cast is fused into the two-shot exchange
+  // (compress.cuh) instead of pushing segment after segment through the slot ring
+  if (compressed && w.desc.compression_flags == 8u && cfg.wire_min_bytes && ubytes >= cfg.wire_min_bytes && P > 1 &&
+      (op == operation::allreduce || op == operation::reduce_scatter || op == operation::allgather)) {
+    const dataType u = static_cast<dataType>(w.udtype), c = static_cast<dataType>(w.cdtype);
+    const bool c16 = c == dataType::float16 || c == dataType::bfloat16;
+    const bool c8 = c == dataType::float8_e4m3 || c == dataType::float8_e5m2;
+    const bool ok = (u == dataType::float32 && (c16 || c8)) || ((u == dataType::float16 || u == dataType::bfloat16) && c8);
+    if (ok && (!c8 || w.ratio_log == 0 || w.ratio_log == 5)) {
+      w.algo = ALGO_WIRE;
+      w.n_ctas = plan_ctas(moved, 128u << 10, cap);
+      return;
     }
   }
   if (eager) {

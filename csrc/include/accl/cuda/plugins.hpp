@@ -16,9 +16,11 @@ class CudaDevice;
 struct GemmRsArgs {
   const void *a;     // [M, K] bf16 row-major (this rank's K-slice of the activations)
   const void *w;     // [N, K] bf16 row-major (this rank's K-slice of the weight, nn.Linear layout)
-  uint64_t out_off;  // heap offset of this rank's [M / P, N] bf16 output shard
+  uint64_t out_off;  // heap offset of this rank's [M / P, N] output shard (bf16, or fp32 with out_f32)
   uint32_t m, n, k;
   uint32_t epoch;    // launch counter (same on every rank), starts at 1
+  int variant = 0;   // 0: automatic, 1: one CTA per 128 x 256 tile, 2: CTA pair (cta_group::2) per 256 x 256 tile
+  bool out_f32 = false; // shard is fp32: the P partial products are added without intermediate rounding
 };
 
 // C = A * W^T computed tile by tile on the 5th-gen tensor cores (TMA ->

@@ -259,5 +259,23 @@ private:
   uint32_t port_;
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Data port for TENSOR-CORE producers ("producer tile writes ... directly into peers"): a kernel that
+// has a finished output tile staged in shared memory (128B-swizzled box of `owner_shard_map`, a CUtensorMap over the
+// owner rank's shard in the peer-mapped symmetric heap) hands it to the reduce-scatter with one instruction: the TMA
+// unit adds the box into the owner's memory over NVLink (cp.reduce.async.bulk.tensor .add, SASS UTMAREDG) — element
+// type and accumulation precision are those of the tensor map (bf16 or fp32).  One thread issues; the staging buffer
+// may be reused once emit_wait_read<N>() says at most N emitted boxes are still being read.
+__device__ __forceinline__ void reduce_scatter_emit_tile(const void *owner_shard_map, const void *smem_tile, int col, int row) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(owner_shard_map)),
+               "r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_tile))), "r"(col), "r"(row)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void emit_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// all boxes emitted by this thread have been added at their owners
+__device__ __forceinline__ void emit_flush() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 } // namespace device
 } // namespace accl

@@ -57,7 +57,7 @@ void bind_cuda(py::module_ &m) {
   // algorithm / channel count a call of `count` elements of `dtype` gets on a communicator of `world` ranks.
   m.def("cuda_plan", [](operation op, uint32_t count, dataType dtype, uint32_t world, uint32_t max_eager_bytes, uint32_t max_ctas,
                         bool has_mc, uint32_t nvls_min_ranks, uint64_t oneshot_max_bytes, bool compressed, uint32_t stage_kb,
-                        uint32_t ll_kb, uint32_t ll_max_bytes, uint32_t ll_oneshot_max) {
+                        uint32_t ll_kb, uint32_t ll_max_bytes, uint32_t ll_oneshot_max, uint32_t staged_max_bytes, bool engine_mode) {
     std::vector<uint32_t> exch(exchmem::SIZE_WORDS, 0);
     exch[exchmem::MAX_EAGER_SIZE / 4] = max_eager_bytes;
     PlanCfg cfg{};
@@ -72,6 +72,8 @@ void bind_cuda(py::module_ &m) {
     cfg.ll_bytes = ll_kb << 10;
     cfg.ll_max_bytes = ll_max_bytes;
     cfg.ll_oneshot_max = ll_oneshot_max;
+    cfg.staged_max_bytes = staged_max_bytes;
+    cfg.engine_mode = engine_mode ? 1 : 0;
     WorkItem w{};
     w.desc.scenario = static_cast<uint32_t>(op);
     w.desc.count = count;
@@ -79,9 +81,9 @@ void bind_cuda(py::module_ &m) {
     w.comm_size = world;
     w.udtype = static_cast<uint32_t>(dtype);
     plan_call(exch.data(), cfg, w);
-    static const char *names[] = {"auto", "local", "eager", "nvls", "p2p", "p2p_oneshot", "ll", "staged"};
+    static const char *names[] = {"auto", "local", "eager", "nvls", "p2p", "p2p_oneshot", "ll", "staged", "wire"};
     py::dict d;
-    d["algo"] = w.algo < 8 ? names[w.algo] : "?";
+    d["algo"] = w.algo < 9 ? names[w.algo] : "?";
     d["n_ctas"] = w.n_ctas;
     d["use_mc"] = (w.flags & WF_USE_MC) != 0;
     d["oneshot"] = (w.flags & WF_ONESHOT) != 0;
@@ -89,7 +91,8 @@ void bind_cuda(py::module_ &m) {
   }, py::arg("op"), py::arg("count"), py::arg("dtype"), py::arg("world"), py::arg("max_eager_bytes") = 65536,
         py::arg("max_ctas") = 128, py::arg("has_mc") = true, py::arg("nvls_min_ranks") = 3,
         py::arg("oneshot_max_bytes") = 2u << 20, py::arg("compressed") = false, py::arg("stage_kb") = 1024, py::arg("ll_kb") = 256,
-        py::arg("ll_max_bytes") = 16384, py::arg("ll_oneshot_max") = 32768);
+        py::arg("ll_max_bytes") = 1 << 20, py::arg("ll_oneshot_max") = 32768, py::arg("staged_max_bytes") = 0,
+        py::arg("engine_mode") = false);
   m.def("cuda_set_tuning", [](ACCL &a, const std::string &name, long value) {
     auto *d = dynamic_cast<CudaDevice *>(a.device());
     if (!d) throw std::runtime_error("not a CUDA backend");
@@ -111,13 +114,17 @@ void bind_cuda(py::module_ &m) {
   });
   // out_shard[M/P, N] (heap buffer, bf16) = reduce_scatter_M( A[M,K] @ W[N,K]^T ), fused on tcgen05 + NVLink
   m.def("gemm_reduce_scatter", [](ACCL &a, uintptr_t a_ptr, uintptr_t w_ptr, BaseBuffer &out, uint32_t M, uint32_t N, uint32_t K,
-                                  uintptr_t stream) {
+                                  uintptr_t stream, int variant) {
     auto *d = dynamic_cast<CudaDevice *>(a.device());
     if (!d) throw std::runtime_error("not a CUDA backend");
     GemmRsArgs g{reinterpret_cast<const void *>(a_ptr), reinterpret_cast<const void *>(w_ptr), out.address(), M, N, K, 0};
+    g.variant = variant;
+    g.out_f32 = out.type() == dataType::float32;
+    if (!g.out_f32 && out.type() != dataType::bfloat16) throw std::invalid_argument("gemm_reduce_scatter: output shard must be bf16 or fp32");
     cudaError_t e = launch_gemm_rs(*d, g, reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) throw std::runtime_error(std::string("gemm_reduce_scatter launch: ") + cudaGetErrorString(e));
-  }, py::call_guard<py::gil_scoped_release>());
+  }, py::arg("accl"), py::arg("a_ptr"), py::arg("w_ptr"), py::arg("out"), py::arg("M"), py::arg("N"), py::arg("K"), py::arg("stream"),
+        py::arg("variant") = 0, py::call_guard<py::gil_scoped_release>());
   // out = allreduce_sum(x + y): the kernel computes and then issues the collective itself (device API -> engine)
   m.def("vadd_allreduce", [](ACCL &a, BaseBuffer &x, BaseBuffer &y, BaseBuffer &tmp, BaseBuffer &out, uint32_t count,
                              uintptr_t status_dev_ptr, uintptr_t stream, uint32_t chunk_elems) {

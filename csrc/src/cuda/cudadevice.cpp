@@ -218,10 +218,10 @@ CudaDevice::CudaDevice(std::shared_ptr<Oob> oob, const CudaConfig &cfg) : oob_(s
     strm_area_ = allocate(cap * N_STRM_PORTS, bufferKind::p2p);
     world_.strm_off = strm_area_->device_addr();
     world_.strm_cap = cap;
-    // staging of the one-way protocols: [bank][parity][source][region]; budget: an eighth of the heap
+    // staging of the one-way protocols: [bank][parity][source][region]; budget: a quarter of the heap
     const size_t regions = static_cast<size_t>(N_BANKS) * 2 * world_.world;
-    const size_t budget = heap_->bytes() / 8 / regions;
-    size_t ll = cfg_.ll_bytes ? cfg_.ll_bytes : std::min<size_t>(512u << 10, budget / 4);
+    const size_t budget = heap_->bytes() / 4 / regions;
+    size_t ll = cfg_.ll_bytes ? cfg_.ll_bytes : std::min<size_t>(2u << 20, budget / 2);
     size_t stg = cfg_.stage_bytes ? cfg_.stage_bytes : std::min<size_t>(2u << 20, budget - std::min(budget, ll));
     ll &= ~static_cast<size_t>(4095);
     stg &= ~static_cast<size_t>(4095);
@@ -438,6 +438,9 @@ PlanCfg CudaDevice::plan_cfg() const {
   c.ll_bytes = static_cast<uint32_t>(world_.ll_bytes);
   c.ll_max_bytes = static_cast<uint32_t>(cfg_.ll_max_bytes);
   c.ll_oneshot_max = static_cast<uint32_t>(cfg_.ll_oneshot_max);
+  c.wire_min_bytes = static_cast<uint32_t>(cfg_.wire_min_bytes);
+  c.staged_max_bytes = static_cast<uint32_t>(cfg_.staged_max_bytes);
+  c.engine_mode = engine_ ? 1u : 0u;
   c.tune = cfg_.tune;
   return c;
 }
@@ -455,6 +458,8 @@ bool CudaDevice::set_tuning(const std::string &name, long v) {
   else if (name == "ll_max_bytes") cfg_.ll_max_bytes = static_cast<size_t>(v);
   else if (name == "ll_oneshot_max") cfg_.ll_oneshot_max = static_cast<size_t>(v);
   else if (name == "oneshot_max_bytes") cfg_.oneshot_max_bytes = static_cast<size_t>(v);
+  else if (name == "wire_min_bytes") cfg_.wire_min_bytes = static_cast<size_t>(v);
+  else if (name == "staged_max_bytes") cfg_.staged_max_bytes = static_cast<size_t>(v);
   else if (name == "stream_loopback") strm_loopback_ = v != 0;
   else return false;
   return true;
@@ -472,6 +477,8 @@ long CudaDevice::get_tuning(const std::string &name) const {
   if (name == "ll_max_bytes") return static_cast<long>(cfg_.ll_max_bytes);
   if (name == "ll_oneshot_max") return static_cast<long>(cfg_.ll_oneshot_max);
   if (name == "oneshot_max_bytes") return static_cast<long>(cfg_.oneshot_max_bytes);
+  if (name == "wire_min_bytes") return static_cast<long>(cfg_.wire_min_bytes);
+  if (name == "staged_max_bytes") return static_cast<long>(cfg_.staged_max_bytes);
   if (name == "stream_loopback") return strm_loopback_ ? 1 : 0;
   if (name == "stage_bytes") return static_cast<long>(world_.stg_bytes);
   if (name == "ll_bytes") return static_cast<long>(world_.ll_bytes);

@@ -29,6 +29,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <stdexcept>
@@ -88,7 +89,7 @@ __device__ void engine_worker(const DevWorld &w, int nworkers) {
           ex = 1;
           break;
         }
-        if (++spins > 16) dev::nanosleep(spins > 2048 ? 400 : 40);
+        if (++spins > 256) dev::nanosleep(spins > 8192 ? 400 : 20);
       }
       s_exit = ex;
       s_err = 0;
@@ -416,7 +417,7 @@ __device__ uint32_t step_call(const EngCtx &e, Call &cl, uint32_t *s_err) {
     }
     return meet_poll(e, cl, false) ? SR_DONE : SR_NOT_READY;
   }
-  if (it.algo == ALGO_LL || it.algo == ALGO_STAGED || it.algo == ALGO_EAGER) {
+  if (it.algo == ALGO_LL || it.algo == ALGO_STAGED || it.algo == ALGO_EAGER || it.algo == ALGO_WIRE) {
     // one-way exchanges: everything they wait for is pushed by the peers at the START of the same collective,
     // so they run to completion — inline when one channel is enough, else as one move on the workers
     if (it.n_ctas <= 1) {
@@ -491,6 +492,7 @@ __device__ void engine_control(const DevWorld &w, HostRing *hr, int nworkers) {
   unsigned long long fetched = me->cmd_fetched;
   unsigned long long host_fetched = me->host_fetched;
   unsigned long long last_work_ns = dev::globaltimer_ns();
+  const uint32_t idle_us = hr->idle_us;
   for (;;) {
     bool progressed = false;
     // ---- fetch new commands while there is room
@@ -573,7 +575,6 @@ __device__ void engine_control(const DevWorld &w, HostRing *hr, int nworkers) {
         me->exch[exchmem::RETCODE / 4] = rc;
         me->exch[exchmem::PERFCNT_LO / 4] = static_cast<uint32_t>(dur);
         if (cl.item.hc_ptr) publish_completion(reinterpret_cast<HostCompletion *>(cl.item.hc_ptr), cl.item.req_seq, rc, dur);
-        __threadfence_system();
         dev::st_release_sys(&me->cmd_status[(cl.ticket1 - 1) % RING_SLOTS], cl.ticket1 | (static_cast<unsigned long long>(rc) << 32));
         me->eng_calls_done += 1;
         cl.active = 0;
@@ -588,20 +589,24 @@ __device__ void engine_control(const DevWorld &w, HostRing *hr, int nworkers) {
       last_work_ns = dev::globaltimer_ns();
       continue;
     }
-    // ---- idle: park after idle_us unless pinned or calls are in flight; leave at once when told to stop
+    // ---- idle: park after idle_us unless pinned or calls are in flight; leave when told to stop.  The host-side
+    // words live in pinned host memory (a PCIe round trip each): they are only looked at after 20 us without work,
+    // so polling the command ring stays a device-memory loop.
     if (t == 0) {
       uint32_t leave = 0;
-      const uint32_t stop = hr->stop;
-      const uint32_t idle_us = hr->idle_us;
-      const bool idle_long = idle_us != 0 && dev::globaltimer_ns() - last_work_ns > static_cast<unsigned long long>(idle_us) * 1000ull;
-      if (stop || (idle_long && hr->pins == 0 && s_nactive == 0)) {
-        hr->state = ENG_EXITING;
-        dev::fence_sc_sys();
-        const bool pending = hr->submitted != host_fetched || dev::ld_acquire_sys(&me->cmd_ready[fetched % RING_SLOTS]) == fetched + 1;
-        if ((pending || s_nactive != 0) && !stop) hr->state = ENG_RUNNING; // a submit raced with parking: keep going
-        else leave = 1;
+      const unsigned long long idle_ns = dev::globaltimer_ns() - last_work_ns;
+      if (idle_ns > 20000ull) {
+        const uint32_t stop = hr->stop;
+        const bool idle_long = idle_us != 0 && idle_ns > static_cast<unsigned long long>(idle_us) * 1000ull;
+        if (stop || (idle_long && s_nactive == 0 && hr->pins == 0)) {
+          hr->state = ENG_EXITING;
+          dev::fence_sc_sys();
+          const bool pending = hr->submitted != host_fetched || dev::ld_acquire_sys(&me->cmd_ready[fetched % RING_SLOTS]) == fetched + 1;
+          if ((pending || s_nactive != 0) && !stop) hr->state = ENG_RUNNING; // a submit raced with parking: keep going
+          else leave = 1;
+        }
+        if (!leave && idle_ns > 100000ull) dev::nanosleep(s_nactive ? 20 : 100); // back off after 100 us of nothing
       }
-      if (!leave) dev::nanosleep(s_nactive ? 20 : 100);
       s_leave = leave;
     }
     __syncthreads();
@@ -631,6 +636,8 @@ __global__ void k_engine_prepare(DevWorld w, PlanCfg cfg, uint32_t timeout_us) {
 // The host-call proxy (hostctrl): places a planned work item in the command ring in stream order and, if
 // `wait_done`, holds the stream until the engine has retired it.
 __global__ void __launch_bounds__(32) k_submit(DevWorld w, WorkItem item, int wait_done) {
+  asm volatile("griddepcontrol.wait;" ::: "memory"); // (programmatic dependent launch, see k_call)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   Ctrl *me = my_ctrl(w);
   EngineArea *ea = engine_area(w);
   unsigned long long t = 0;
@@ -651,7 +658,7 @@ __global__ void __launch_bounds__(32) k_submit(DevWorld w, WorkItem item, int wa
       uint32_t spins = 0;
       // (>=: a later occupant of the slot may have retired already if 128 calls overtook a parked one)
       while (static_cast<int32_t>(static_cast<uint32_t>(dev::ld_acquire_sys(st)) - static_cast<uint32_t>(t + 1)) < 0)
-        if (++spins > 4) dev::nanosleep(spins > 256 ? 200 : 20);
+        if (++spins > 64) dev::nanosleep(spins > 1024 ? 200 : 20);
     }
   }
 }
@@ -661,6 +668,11 @@ __global__ void __launch_bounds__(32) k_submit(DevWorld w, WorkItem item, int wa
 // device function with the engine above (one translation unit, one copy).
 __global__ void __launch_bounds__(k::BLOCK) k_call(DevWorld w, WorkItem it, HostCompletion *hc) {
   __shared__ uint32_t s_err;
+  // Programmatic dependent launch: this kernel may have been scheduled while its predecessor on the stream was still
+  // draining (the launch latency of back-to-back collectives overlaps the previous one's tail); nothing is read
+  // before the predecessor has completed.  The successor is released right after, so at most one is ever pre-staged.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const unsigned long long t0 = dev::globaltimer_ns();
   if (threadIdx.x == 0) s_err = 0;
   __syncthreads();
@@ -703,8 +715,20 @@ __global__ void __launch_bounds__(k::BLOCK) k_call(DevWorld w, WorkItem it, Host
 }
 
 cudaError_t launch_call(const DevWorld &w, const WorkItem &item, HostCompletion *hc_dev, cudaStream_t stream) {
-  k_call<<<item.n_ctas, k::BLOCK, 0, stream>>>(w, item, hc_dev);
-  return cudaGetLastError();
+  static const bool pdl = [] {
+    const char *e = std::getenv("ACCL_PDL");
+    return !e || std::atoi(e) != 0;
+  }();
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(item.n_ctas);
+  lc.blockDim = dim3(k::BLOCK);
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&lc, k_call, w, item, hc_dev);
 }
 
 __global__ void k_reset_ctrl(DevWorld w) {
@@ -876,8 +900,16 @@ void Engine::submit(const WorkItem &w, HostCompletion *hc, cudaStream_t s, bool 
   r->submitted = impl_->submitted;
   std::atomic_thread_fence(std::memory_order_seq_cst);
   ensure_running_locked();
-  k_submit<<<1, 32, 0, s>>>(dev_.world(), item, stream_waits ? 1 : 0);
-  ACCL_CUDART(cudaGetLastError());
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(1);
+  lc.blockDim = dim3(32);
+  lc.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  ACCL_CUDART(cudaLaunchKernelEx(&lc, k_submit, dev_.world(), item, stream_waits ? 1 : 0));
 }
 
 } // namespace cuda

@@ -4,7 +4,14 @@
 // W_r [N, K_r] (bf16, K contiguous).  The full product is C = sum_r A_r W_r^T,
 // reduce-scattered along M: rank o ends up with rows [o*M/P, (o+1)*M/P).
 //
-// One persistent, warp-specialised sm_100a kernel per rank:
+// One persistent, warp-specialised sm_100a kernel per rank, in two flavours selected at run time
+// (GemmRsArgs::variant, default: the CTA pair when the shape allows it):
+//   * single CTA per 128 x 256 tile (tcgen05.mma cta_group::1, 4-stage ring), and
+//   * CTA PAIR per 256 x 256 tile (cluster of 2, tcgen05.mma cta_group::2 with M = 256: each CTA loads 128 rows of A
+//     and 128 rows of W per stage — 32 KB instead of 48 KB, so 6 stages fit and W is fetched once per 256 rows),
+// each with a bf16 or an fp32 reduction of the partial tiles (the TMA unit adds in the shard's element type: fp32
+// shards accumulate the P partial products without intermediate rounding).
+// Roles of the 8 warps of a CTA:
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of 128x64 (A) and
 //               256x64 (W) bf16 tiles, 128B-swizzled, into a 4-stage smem ring,
 //               signalling mbarriers with complete_tx
@@ -40,6 +47,7 @@
 #include "accl/cuda/cudadevice.hpp"
 #include "accl/cuda/driver_api.hpp"
 #include "accl/cuda/plugins.hpp"
+#include "accl/device/api.cuh"
 #include "kernels.cuh"
 
 namespace accl {
@@ -155,7 +163,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(uint32_t lo_f32, uint32_t hi_f32
 } // namespace g
 
 struct alignas(64) OutMaps {
-  CUtensorMap m[ACCL_MAX_RANKS]; // owner rank o: its [M/P, N] bf16 shard through my peer mapping
+  CUtensorMap m[ACCL_MAX_RANKS]; // owner rank o: its [M/P, N] shard through my peer mapping
 };
 
 struct GemmRsParams {
@@ -167,16 +175,109 @@ struct GemmRsParams {
   unsigned int *grid_flags; // zeroed before every launch: [0] zero-phase arrivals, [1] release, [2] finished CTAs, [3] error, [8..] peer offsets
 };
 
+namespace g {
+// ---- CTA-pair (cta_group::2) flavours of the primitives
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same object in the pair's leader (cluster rank 0)
+__device__ __forceinline__ uint32_t leader_addr(const void *p) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(p)));
+  return r;
+}
+// issued by both CTAs; the transaction bytes are accounted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_addr(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+}
+
+template <bool PAIR> struct Cfg {
+  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int BN_LOAD = PAIR ? BN / 2 : BN;          // W rows this CTA loads per stage
+  static constexpr int B_STAGE = BN_LOAD * BK * 2;
+  static constexpr int STAGE = A_STAGE_BYTES + B_STAGE;
+  static constexpr int SMEM = STAGES * STAGE + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TILE_M = PAIR ? 2 * BM : BM;           // rows of one output tile
+};
+} // namespace g
+
+// One epilogue chunk: 32 accumulator rows (this warp's TMEM lanes) x COLS columns -> staged in 128B-swizzled
+// shared memory -> handed to the collective (device API: reduce_scatter_emit_tile).
+template <bool F32>
+__device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint8_t *buf, int lane) {
+  using namespace g;
+  uint32_t r[32];
+  if (F32) {
+    // 32 fp32 columns = one 128-byte row per lane
+    tmem_ld_32x32(taddr, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t chunk = static_cast<uint32_t>(j) ^ (lane & 7u); // XOR swizzle of the 16-byte chunk with the row
+      *reinterpret_cast<uint4 *>(buf + lane * 128 + chunk * 16) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      tmem_ld_32x32(taddr + h * 32, r);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t chunk = static_cast<uint32_t>(h * 4 + j) ^ (lane & 7u);
+        uint4 v;
+        v.x = pack_bf16x2(r[8 * j + 0], r[8 * j + 1]);
+        v.y = pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
+        v.z = pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
+        v.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
+        *reinterpret_cast<uint4 *>(buf + lane * 128 + chunk * 16) = v;
+      }
+    }
+  }
+}
+
+template <bool PAIR, bool F32>
 __global__ void __launch_bounds__(g::THREADS, 1)
 k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ OutMaps out_maps, GemmRsParams p) {
   using namespace g;
+  using C = Cfg<PAIR>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int COLS = F32 ? 32 : 64; // columns per emitted box: one 128-byte swizzle row
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t *smem_a = smem;
   uint8_t *smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint8_t *smem_epi = smem + STAGES * STAGE_BYTES;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+  uint8_t *smem_epi = smem + STAGES * C::STAGE;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * C::STAGE + EPI_BYTES);
   uint64_t *full = bars, *empty = bars + STAGES, *tmem_full = bars + 2 * STAGES, *tmem_empty = bars + 2 * STAGES + ACC_STAGES;
   uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2 * ACC_STAGES);
 
@@ -186,8 +287,10 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __shared__ uint64_t s_off0[ACCL_MAX_RANKS], s_off2[ACCL_MAX_RANKS];
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t cr = PAIR ? cluster_ctarank() : 0; // 0 = leader of the pair
+  const uint32_t unit = PAIR ? blockIdx.x / 2 : blockIdx.x, num_units = PAIR ? gridDim.x / 2 : gridDim.x;
   const uint32_t P = p.w.world, me = p.w.rank;
-  const uint32_t tiles_m = p.m / BM, tiles_n = p.n / BN, num_tiles = tiles_m * tiles_n;
+  const uint32_t tiles_m = p.m / C::TILE_M, tiles_n = p.n / BN, num_tiles = tiles_m * tiles_n;
   const uint32_t k_blocks = p.k / BK;
   const uint32_t rows_per_rank = p.m / P, tiles_m_per_rank = tiles_m / P;
   char *my_heap = p.w.window + static_cast<uint64_t>(me) * p.w.heap_bytes;
@@ -196,12 +299,12 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (threadIdx.x == 0) {
     s_err = 0;
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&full[i], 1);  // the producer's arrive.expect_tx (pair: the leader's; the peer's copy is never used)
+      mbar_init(&empty[i], 1); // tcgen05.commit (pair: the leader's multicast commit)
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4); // one arrival per epilogue warp
+      mbar_init(&tmem_empty[i], PAIR ? 8 : 4); // one arrival per epilogue warp (pair: of both CTAs, on the leader)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -218,11 +321,17 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync(); // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -230,7 +339,7 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   {
     dev::Vec16 z{0, 0, 0, 0};
     char *shard = my_heap + p.out_off;
-    const size_t nvec = static_cast<size_t>(rows_per_rank) * p.n * 2 / 16;
+    const size_t nvec = static_cast<size_t>(rows_per_rank) * p.n * (F32 ? 4 : 2) / 16;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += static_cast<size_t>(gridDim.x) * blockDim.x)
       dev::st_stream(shard + i * 16, z);
     __threadfence();
@@ -252,24 +361,30 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (threadIdx.x < P) reinterpret_cast<volatile uint64_t *>(p.grid_flags + 8)[threadIdx.x] = s_off0[threadIdx.x];
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
-      atomicExch(&p.grid_flags[1], 1u); // release the epilogues of every CTA
-    }
+    if (threadIdx.x == 0) atomicExch(&p.grid_flags[1], 1u); // release the epilogues of every CTA
   }
 
   // ---------------- warp-specialised main loop
   if (warp == 0) {
-    // ===== TMA producer
+    // ===== TMA producer (pair: both CTAs, each its 128 rows of A and its 128 rows of W)
     uint32_t stage = 0, phase = 0;
-    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (uint32_t t = unit; t < num_tiles; t += num_units) {
       const uint32_t mo = t / tiles_n, nb = t % tiles_n;
       const uint32_t mb = (mo + (me + 1) * tiles_m_per_rank) % tiles_m; // peers' rows first, mine last
       for (uint32_t kb = 0; kb < k_blocks; ++kb) {
         if (lane == 0) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], STAGE_BYTES);
-          tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full[stage], static_cast<int>(kb * BK), static_cast<int>(mb * BM));
-          tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full[stage], static_cast<int>(kb * BK), static_cast<int>(nb * BN));
+          if (PAIR) {
+            if (cr == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE); // both CTAs' loads land on the leader's barrier
+            tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full[stage], static_cast<int>(kb * BK),
+                             static_cast<int>(mb * C::TILE_M + cr * BM));
+            tma_load_2d_pair(smem_b + stage * C::B_STAGE, &tmap_b, &full[stage], static_cast<int>(kb * BK),
+                             static_cast<int>(nb * BN + cr * C::BN_LOAD));
+          } else {
+            mbar_expect_tx(&full[stage], C::STAGE);
+            tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full[stage], static_cast<int>(kb * BK), static_cast<int>(mb * BM));
+            tma_load_2d(smem_b + stage * C::B_STAGE, &tmap_b, &full[stage], static_cast<int>(kb * BK), static_cast<int>(nb * BN));
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -278,13 +393,13 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer
-    const uint32_t idesc = make_idesc(BM, BN);
+  } else if (warp == 1 && cr == 0) {
+    // ===== MMA issuer (pair: the leader only)
+    const uint32_t idesc = make_idesc(C::TILE_M, BN);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (uint32_t t = unit; t < num_tiles; t += num_units) {
       if (lane == 0) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1); // epilogue has drained this accumulator
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1); // epilogue(s) have drained this accumulator
         tc_fence_after();
       }
       __syncwarp();
@@ -293,12 +408,19 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
-          const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+          const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * C::B_STAGE));
 #pragma unroll
-          for (int kk = 0; kk < BK / UMMA_K; ++kk) // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
-            umma_f16(tmem_base + acc * BN, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
-          umma_commit(&empty[stage]); // smem stage reusable once these MMAs retire
-          if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) { // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
+            if (PAIR) umma_f16_pair(tmem_base + acc * BN, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+            else umma_f16(tmem_base + acc * BN, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+          }
+          if (PAIR) {
+            umma_commit_pair(&empty[stage]); // smem stage reusable (in both CTAs) once these MMAs retire
+            if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[acc]);
+          } else {
+            umma_commit(&empty[stage]);
+            if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -312,7 +434,7 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> bf16 -> swizzled smem -> TMA reduce-add into the owner's shard
+    // ===== epilogue: TMEM -> registers -> shard element type -> swizzled smem -> emitted into the collective
     const uint32_t ew = warp - 4; // == warp % 4: this warp owns TMEM lanes [32*ew, 32*ew+32)
     if (lane == 0) {
       uint32_t spins = 0;
@@ -325,51 +447,38 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane < P && reinterpret_cast<const volatile uint64_t *>(p.grid_flags + 8)[lane] != p.out_off) atomicOr(&p.grid_flags[3], static_cast<unsigned>(DMA_MISMATCH_ERROR));
     uint8_t *my_epi = smem_epi + ew * 2 * EPI_BUF_BYTES;
     uint32_t acc = 0, acc_phase = 0, ebuf = 0;
-    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (uint32_t t = unit; t < num_tiles; t += num_units) {
       const uint32_t mo = t / tiles_n, nb = t % tiles_n;
       const uint32_t mb = (mo + (me + 1) * tiles_m_per_rank) % tiles_m;
-      const uint32_t row0 = mb * BM + ew * 32;     // first of this warp's 32 rows
-      const uint32_t owner = row0 / rows_per_rank; // a warp's rows never straddle owners
+      const uint32_t row0 = mb * C::TILE_M + cr * BM + ew * 32; // first of this warp's 32 rows
+      const uint32_t owner = row0 / rows_per_rank;               // a warp's rows never straddle owners
       const int local_row0 = static_cast<int>(row0 - owner * rows_per_rank);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / EPI_COLS; ++c) {
+      for (int c = 0; c < BN / COLS; ++c) {
         uint8_t *buf = my_epi + ebuf * EPI_BUF_BYTES;
         // the TMA unit must be done READING this buffer (issued two chunks ago)
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (lane == 0) device::emit_wait_read<1>();
         __syncwarp();
-        uint32_t r[32];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          tmem_ld_32x32(tmem_base + ((ew * 32u) << 16) + acc * BN + c * EPI_COLS + h * 32, r);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            // 16-byte chunk index inside the 128-byte row, XOR-swizzled with the row (SWIZZLE_128B)
-            const uint32_t chunk = static_cast<uint32_t>(h * 4 + j) ^ (lane & 7u);
-            uint4 v;
-            v.x = pack_bf16x2(r[8 * j + 0], r[8 * j + 1]);
-            v.y = pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
-            v.z = pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
-            v.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
-            *reinterpret_cast<uint4 *>(buf + lane * 128 + chunk * 16) = v;
-          }
-        }
+        epilogue_chunk<F32>(tmem_base + ((ew * 32u) << 16) + acc * BN + c * COLS, buf, lane);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the TMA unit
         __syncwarp();
-        if (lane == 0)
-          tma_reduce_add_2d(&out_maps.m[owner], buf, static_cast<int>(nb * BN + c * EPI_COLS), local_row0);
+        if (lane == 0) device::reduce_scatter_emit_tile(&out_maps.m[owner], buf, static_cast<int>(nb * BN + c * COLS), local_row0);
         ebuf ^= 1;
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&tmem_empty[acc]);
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == ACC_STAGES) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // all my reductions have completed
+    if (lane == 0) device::emit_flush(); // all my reductions have completed
     __syncwarp();
     __threadfence_system(); // my adds are performed before this CTA reports completion
   }
@@ -377,8 +486,10 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // ---------------- teardown: free TMEM; the last CTA of the grid meets the peers again
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync(); // nobody frees TMEM or exits while the peer may still signal its barriers
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
   __shared__ uint32_t s_last;
   if (threadIdx.x == 0) {
@@ -392,301 +503,6 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (threadIdx.x == 0 && s_err) atomicOr(&p.grid_flags[3], s_err);
   }
 }
-
-
-#ifdef ACCL_EXPERIMENTAL_GEMM_2CTA
-// =====================================================================================================
-// EXPERIMENTAL (compiled out by default, not yet validated on hardware; docs/roadmap.md #4).
-// CTA-pair variant: two CTAs of a cluster (one TPC) own one 256 x 256 output tile.  CTA r of the pair
-// loads rows [128 r, 128 r + 128) of the A tile and rows [128 r, 128 r + 128) of the W tile (its half of
-// N); the leader (cluster rank 0) issues tcgen05.mma.cta_group::2 with M = 256, N = 256, which reads both
-// halves of both operands from the two shared memories and leaves rows 128 r.. of the accumulator in
-// CTA r's TMEM.  Per stage and CTA: 16 KB of A + 16 KB of W instead of 16 + 32 -> 6 stages instead of 4
-// in the same shared memory, and W is fetched once per 256 rows instead of once per 128.
-// Barriers: the leader's `full` counts the bytes of all four loads (both CTAs signal it: peer bit of the
-// barrier address cleared); `empty` and `tmem_full` exist in both CTAs and are arrived by the leader's
-// multicast tcgen05.commit; the leader's `tmem_empty` collects the 8 epilogue warps of the pair.
-namespace g2 {
-constexpr int BM = 128, BN = 256, BNH = 128, BK = 64; // per-CTA A rows, tile N, per-CTA W rows
-constexpr int STAGES = 6, ACC_STAGES = 2;
-constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BNH * BK * 2;  // 16 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + g::EPI_BYTES + 1024 + 256;
-constexpr uint32_t PEER_MASK = 0xFEFFFFFFu; // shared::cluster address of the same object in the pair's leader
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// issued by both CTAs; the transaction bytes are accounted on the LEADER's barrier
-__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *leader_bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          g::smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(g::smem_u32(leader_bar) & PEER_MASK), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on the barrier at this shared-memory offset in BOTH CTAs once the MMAs issued so far have retired
-__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
-  const uint16_t mask = 3;
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   g::smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(g::smem_u32(bar) & PEER_MASK) : "memory");
-}
-} // namespace g2
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g::THREADS, 1)
-k_plugin_gemm_rs_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                      const __grid_constant__ OutMaps out_maps, GemmRsParams p) {
-  using namespace g2;
-  using g::mbar_arrive;
-  using g::mbar_expect_tx;
-  using g::mbar_init;
-  using g::mbar_wait;
-  using g::smem_u32;
-  using g::tc_fence_after;
-  using g::tc_fence_before;
-  constexpr int THREADS = g::THREADS, TMEM_COLS = g::TMEM_COLS, UMMA_K = g::UMMA_K, EPI_COLS = g::EPI_COLS,
-                EPI_BUF_BYTES = g::EPI_BUF_BYTES, EPI_BYTES = g::EPI_BYTES;
-  (void)THREADS;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t *smem_a = smem;
-  uint8_t *smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint8_t *smem_epi = smem + STAGES * STAGE_BYTES;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
-  uint64_t *full = bars, *empty = bars + STAGES, *tmem_full = bars + 2 * STAGES, *tmem_empty = bars + 2 * STAGES + ACC_STAGES;
-  uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2 * ACC_STAGES);
-
-  __shared__ uint32_t s_err;
-  __shared__ k::PtrTable s_tab;
-  __shared__ WorkItem s_item;
-  __shared__ uint64_t s_off0[ACCL_MAX_RANKS], s_off2[ACCL_MAX_RANKS];
-
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const uint32_t cr = cluster_ctarank(); // 0 = leader
-  const uint32_t pair = blockIdx.x / 2, num_pairs = gridDim.x / 2;
-  const uint32_t P = p.w.world, me = p.w.rank;
-  const uint32_t tiles_m = p.m / (2 * BM), tiles_n = p.n / BN, num_tiles = tiles_m * tiles_n; // 256 x 256 tiles
-  const uint32_t k_blocks = p.k / BK;
-  const uint32_t rows_per_rank = p.m / P, tiles_m_per_rank = tiles_m / P;
-  char *my_heap = p.w.window + static_cast<uint64_t>(me) * p.w.heap_bytes;
-
-  if (threadIdx.x == 0) {
-    s_err = 0;
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 1);  // leader: its producer's arrive.expect_tx (the peer's copy is never used)
-      mbar_init(&empty[i], 1); // the leader's multicast commit
-    }
-    for (int i = 0; i < ACC_STAGES; ++i) {
-      mbar_init(&tmem_full[i], 1);  // the leader's multicast commit
-      mbar_init(&tmem_empty[i], 8); // leader: 4 epilogue warps of each CTA of the pair
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    s_item.comm_size = P;
-    s_item.comm_rank = me;
-    for (uint32_t r = 0; r < static_cast<uint32_t>(ACCL_MAX_RANKS); ++r) s_item.members[r] = static_cast<uint8_t>(r < P ? r : 0);
-    s_item.desc.scenario = 0x47;
-    s_item.timeout_us = p.timeout_us;
-    s_item.bank = 0;
-    s_item.comm_sig = 0x47454Du;
-  }
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
-  }
-  if (warp == 2) { // the same warp in both CTAs, same slot address
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync(); // the peer's barriers are initialised before anything signals them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
-
-  // ---------------- zero my output shard, then meet the peers (identical to the single-CTA kernel)
-  {
-    dev::Vec16 z{0, 0, 0, 0};
-    char *shard = my_heap + p.out_off;
-    const size_t nvec = static_cast<size_t>(rows_per_rank) * p.n * 2 / 16;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-      dev::st_stream(shard + i * 16, z);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(&p.grid_flags[0], 1u);
-  }
-  if (blockIdx.x == 0 && warp == 3) {
-    if (lane == 0)
-      while (atomicAdd(&p.grid_flags[0], 0u) < gridDim.x) dev::nanosleep(100);
-    __syncwarp();
-    __threadfence();
-  }
-  k::Ctx ctx{p.w, s_item, MAX_CH - 1, 1, reinterpret_cast<Ctrl *>(my_heap), &s_err, static_cast<uint64_t>(p.timeout_us) * 1000ull, &s_tab};
-  if (blockIdx.x == 0) {
-    __syncthreads();
-    k::chan_sync(ctx, true, p.out_off, p.out_off, s_off0, s_off2);
-    if (threadIdx.x < P) reinterpret_cast<volatile uint64_t *>(p.grid_flags + 8)[threadIdx.x] = s_off0[threadIdx.x];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicExch(&p.grid_flags[1], 1u);
-  }
-
-  if (warp == 0) {
-    // ===== TMA producer (both CTAs): my 128 rows of A, my 128 rows of W
-    uint32_t stage = 0, phase = 0;
-    for (uint32_t t = pair; t < num_tiles; t += num_pairs) {
-      const uint32_t mo = t / tiles_n, nb = t % tiles_n;
-      const uint32_t mb = (mo + (me + 1) * tiles_m_per_rank) % tiles_m; // peers' rows first, mine last
-      for (uint32_t kb = 0; kb < k_blocks; ++kb) {
-        if (lane == 0) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (cr == 0) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES); // both CTAs' loads land on the leader's barrier
-          tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full[stage], static_cast<int>(kb * BK),
-                           static_cast<int>(mb * 2 * BM + cr * BM));
-          tma_load_2d_pair(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full[stage], static_cast<int>(kb * BK),
-                           static_cast<int>(nb * BN + cr * BNH));
-        }
-        __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1 && cr == 0) {
-    // ===== MMA issuer (leader only)
-    const uint32_t idesc = g::make_idesc(2 * BM, BN);
-    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (uint32_t t = pair; t < num_tiles; t += num_pairs) {
-      if (lane == 0) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1); // both epilogues have drained this accumulator
-        tc_fence_after();
-      }
-      __syncwarp();
-      for (uint32_t kb = 0; kb < k_blocks; ++kb) {
-        if (lane == 0) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint64_t da = g::make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
-          const uint64_t db = g::make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
-#pragma unroll
-          for (int kk = 0; kk < BK / UMMA_K; ++kk)
-            umma_f16_pair(tmem_base + acc * BN, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
-          umma_commit_pair(&empty[stage]);
-          if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[acc]);
-        }
-        __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-      if (++acc == ACC_STAGES) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-    }
-  } else if (warp >= 4) {
-    // ===== epilogue (both CTAs): my 128 rows of the 256-row tile
-    const uint32_t ew = warp - 4;
-    if (lane == 0) {
-      uint32_t spins = 0;
-      while (*reinterpret_cast<volatile unsigned int *>(&p.grid_flags[1]) == 0)
-        if (++spins > 64) dev::nanosleep(200);
-    }
-    __syncwarp();
-    __threadfence();
-    if (lane < P && reinterpret_cast<const volatile uint64_t *>(p.grid_flags + 8)[lane] != p.out_off) atomicOr(&p.grid_flags[3], static_cast<unsigned>(DMA_MISMATCH_ERROR));
-    uint8_t *my_epi = smem_epi + ew * 2 * EPI_BUF_BYTES;
-    uint32_t acc = 0, acc_phase = 0, ebuf = 0;
-    for (uint32_t t = pair; t < num_tiles; t += num_pairs) {
-      const uint32_t mo = t / tiles_n, nb = t % tiles_n;
-      const uint32_t mb = (mo + (me + 1) * tiles_m_per_rank) % tiles_m;
-      const uint32_t row0 = mb * 2 * BM + cr * BM + ew * 32;
-      const uint32_t owner = row0 / rows_per_rank;
-      const int local_row0 = static_cast<int>(row0 - owner * rows_per_rank);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / EPI_COLS; ++c) {
-        uint8_t *buf = my_epi + ebuf * EPI_BUF_BYTES;
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncwarp();
-        uint32_t r[32];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          g::tmem_ld_32x32(tmem_base + ((ew * 32u) << 16) + acc * BN + c * EPI_COLS + h * 32, r);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t chunk = static_cast<uint32_t>(h * 4 + j) ^ (lane & 7u);
-            uint4 v;
-            v.x = g::pack_bf16x2(r[8 * j + 0], r[8 * j + 1]);
-            v.y = g::pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
-            v.z = g::pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
-            v.w = g::pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
-            *reinterpret_cast<uint4 *>(buf + lane * 128 + chunk * 16) = v;
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0)
-          g::tma_reduce_add_2d(&out_maps.m[owner], buf, static_cast<int>(nb * BN + c * EPI_COLS), local_row0);
-        ebuf ^= 1;
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
-      if (++acc == ACC_STAGES) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-    }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    __syncwarp();
-    __threadfence_system();
-  }
-
-  // ---------------- teardown
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync(); // nobody frees TMEM or exits while the peer may still signal its barriers
-  if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
-  }
-  __shared__ uint32_t s_last;
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    s_last = atomicAdd(&p.grid_flags[2], 1u) == gridDim.x - 1 ? 1u : 0u;
-  }
-  __syncthreads();
-  if (s_last) {
-    k::chan_sync(ctx, false, 0, 0, nullptr, nullptr);
-    if (threadIdx.x == 0 && s_err) atomicOr(&p.grid_flags[3], s_err);
-  }
-}
-#endif // ACCL_EXPERIMENTAL_GEMM_2CTA
 
 // ----------------------------------------------------------------------- host
 namespace {
@@ -704,15 +520,16 @@ EncodeFn encode_fn() {
   return fn;
 }
 
-CUtensorMap make_map(const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+CUtensorMap make_map(const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols, bool f32 = false) {
   CUtensorMap m;
+  const uint64_t es = f32 ? 4 : 2;
   const cuuint64_t dims[2] = {cols, rows};           // innermost first
-  const cuuint64_t strides[1] = {cols * 2};          // bytes between rows
+  const cuuint64_t strides[1] = {cols * es};         // bytes between rows
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode_fn()(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + cu_error_string(r));
   return m;
 }
@@ -722,15 +539,52 @@ struct PluginState {
 };
 std::mutex g_state_m;
 std::map<CudaDevice *, PluginState> g_state;
+
+template <bool PAIR, bool F32> void set_smem_attr() {
+  cudaFuncSetAttribute(k_plugin_gemm_rs<PAIR, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, g::Cfg<PAIR>::SMEM);
+}
 } // namespace
 
 void preload_gemm_rs_kernels() {
   cudaFuncAttributes a;
-#ifdef ACCL_EXPERIMENTAL_GEMM_2CTA
-  cudaFuncGetAttributes(&a, k_plugin_gemm_rs_2cta);
-#endif
-  cudaFuncGetAttributes(&a, k_plugin_gemm_rs);
-  cudaFuncSetAttribute(k_plugin_gemm_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, g::SMEM_BYTES);
+  cudaFuncGetAttributes(&a, k_plugin_gemm_rs<false, false>);
+  cudaFuncGetAttributes(&a, k_plugin_gemm_rs<false, true>);
+  cudaFuncGetAttributes(&a, k_plugin_gemm_rs<true, false>);
+  cudaFuncGetAttributes(&a, k_plugin_gemm_rs<true, true>);
+  set_smem_attr<false, false>();
+  set_smem_attr<false, true>();
+  set_smem_attr<true, false>();
+  set_smem_attr<true, true>();
+}
+
+template <bool PAIR, bool F32>
+static cudaError_t launch_variant(const CUtensorMap &ta, const CUtensorMap &tb, const OutMaps &om, const GemmRsParams &p, uint32_t tiles,
+                                  int sms, cudaStream_t stream) {
+  using namespace g;
+  set_smem_attr<PAIR, F32>();
+  cudaLaunchConfig_t lc = {};
+  lc.blockDim = dim3(THREADS);
+  lc.dynamicSmemBytes = Cfg<PAIR>::SMEM;
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  if (PAIR) {
+    uint32_t pairs = std::min<uint32_t>(static_cast<uint32_t>(sms) / 2, tiles);
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    lc.gridDim = dim3(2 * pairs);
+    // the kernel spins on grid-wide flags: every cluster must be resident at once
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, k_plugin_gemm_rs<PAIR, F32>, &lc) == cudaSuccess && max_clusters > 0)
+      pairs = std::min<uint32_t>(pairs, static_cast<uint32_t>(max_clusters));
+    lc.gridDim = dim3(2 * pairs);
+  } else {
+    lc.gridDim = dim3(std::min<uint32_t>(static_cast<uint32_t>(sms), tiles));
+  }
+  return cudaLaunchKernelEx(&lc, k_plugin_gemm_rs<PAIR, F32>, ta, tb, om, p);
 }
 
 cudaError_t launch_gemm_rs(CudaDevice &dev, const GemmRsArgs &a, cudaStream_t stream) {
@@ -748,14 +602,24 @@ cudaError_t launch_gemm_rs(CudaDevice &dev, const GemmRsArgs &a, cudaStream_t st
       ACCL_CUDART(cudaMemset(st->flags, 0, 64 * sizeof(unsigned int)));
     }
   }
-  cudaFuncSetAttribute(k_plugin_gemm_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  // CTA-pair kernel: 256-row tiles must not straddle shard owners.  variant: 0 = automatic, 1 = single CTA, 2 = pair;
+  // ACCL_GEMM_VARIANT overrides the automatic choice.
+  static const int env_variant = [] {
+    const char *e = std::getenv("ACCL_GEMM_VARIANT");
+    return e ? std::atoi(e) : 0;
+  }();
+  int variant = a.variant ? a.variant : env_variant;
+  const bool pair_ok = a.m % (2 * BM * P) == 0;
+  if (variant == 2 && !pair_ok) throw std::invalid_argument("gemm_rs: the CTA-pair kernel needs M % (256*world) == 0");
+  const bool pair = variant == 2 || (variant == 0 && pair_ok);
+  const bool f32 = a.out_f32;
   const CUtensorMap ta = make_map(a.a, a.m, a.k, BM, BK);
-  const CUtensorMap tb = make_map(a.w, a.n, a.k, BN, BK);
+  const CUtensorMap tb = make_map(a.w, a.n, a.k, pair ? BN / 2 : BN, BK); // each CTA of a pair loads half of the N tile
   OutMaps om;
   std::memset(&om, 0, sizeof(om));
   for (uint32_t o = 0; o < P; ++o) // symmetric allocation: the shard sits at out_off in every heap (verified in-kernel)
     om.m[o] = make_map(dev.world().window + static_cast<uint64_t>(o) * dev.world().heap_bytes + a.out_off, a.m / P, a.n, 32,
-                       EPI_COLS);
+                       f32 ? 32 : EPI_COLS, f32);
   GemmRsParams p;
   p.w = dev.world();
   p.out_off = a.out_off;
@@ -768,40 +632,9 @@ cudaError_t launch_gemm_rs(CudaDevice &dev, const GemmRsArgs &a, cudaStream_t st
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev.device());
   ACCL_CUDART(cudaMemsetAsync(st->flags, 0, 64 * sizeof(unsigned int), stream));
-#ifdef ACCL_EXPERIMENTAL_GEMM_2CTA
-  // CTA-pair kernel: 256-row tiles must not straddle shard owners; opt out with ACCL_GEMM_2CTA=0
-  static const bool want_pair = [] {
-    const char *e = std::getenv("ACCL_GEMM_2CTA");
-    return !e || std::atoi(e) != 0;
-  }();
-  if (want_pair && a.m % (2 * BM * P) == 0) {
-    cudaFuncSetAttribute(k_plugin_gemm_rs_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, g2::SMEM_BYTES);
-    const CUtensorMap tb2 = make_map(a.w, a.n, a.k, g2::BNH, BK); // each CTA of a pair loads half of the N tile
-    const uint32_t tiles2 = (a.m / (2 * BM)) * (a.n / BN);
-    uint32_t pairs = std::min<uint32_t>(static_cast<uint32_t>(sms) / 2, tiles2);
-    // the kernel spins on grid-wide flags: every cluster must be resident at once
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(2 * pairs);
-    lc.blockDim = dim3(THREADS);
-    lc.dynamicSmemBytes = g2::SMEM_BYTES;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    lc.attrs = at;
-    lc.numAttrs = 1;
-    int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, k_plugin_gemm_rs_2cta, &lc) == cudaSuccess && max_clusters > 0)
-      pairs = std::min<uint32_t>(pairs, static_cast<uint32_t>(max_clusters));
-    k_plugin_gemm_rs_2cta<<<2 * pairs, THREADS, g2::SMEM_BYTES, stream>>>(ta, tb2, om, p);
-    return cudaGetLastError();
-  }
-#endif
-  const uint32_t tiles = (a.m / BM) * (a.n / BN);
-  const uint32_t grid = std::min<uint32_t>(static_cast<uint32_t>(sms), tiles);
-  k_plugin_gemm_rs<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, om, p);
-  return cudaGetLastError();
+  const uint32_t tiles = (a.m / (pair ? 2 * BM : BM)) * (a.n / BN);
+  if (pair) return f32 ? launch_variant<true, true>(ta, tb, om, p, tiles, sms, stream) : launch_variant<true, false>(ta, tb, om, p, tiles, sms, stream);
+  return f32 ? launch_variant<false, true>(ta, tb, om, p, tiles, sms, stream) : launch_variant<false, false>(ta, tb, om, p, tiles, sms, stream);
 }
 
 } // namespace cuda

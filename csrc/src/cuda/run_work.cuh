@@ -2,6 +2,7 @@
 #pragma once
 #include "collectives.cuh"
 #include "staged.cuh"
+#include "compress.cuh"
 
 namespace accl {
 namespace cuda {
@@ -29,6 +30,10 @@ __device__ __noinline__ void run_work(const DevWorld &w, const WorkItem &it, int
     case operation::alltoall: stg_collective(c, SP_ALLTOALL, &s_tmp); return;
     default: break;
     }
+  }
+  if (it.algo == ALGO_WIRE) {
+    wire_collective(c);
+    return;
   }
   switch (op) {
   case operation::nop:

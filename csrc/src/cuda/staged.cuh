@@ -175,15 +175,19 @@ __device__ __forceinline__ void stg_open(const Ctx &c, const StgRoles &ro, uint3
   if (t < ro.P) {
     StageBank &sb = c.stg();
     const uint32_t peer = c.g(t);
+    // three independent loads in flight together (each is an L2 round trip on the call's critical path)
+    const uint32_t sent = *reinterpret_cast<volatile uint32_t *>(&sb.sent[ch][peer]);
+    const uint32_t recvd = *reinterpret_cast<volatile uint32_t *>(&sb.recvd[ch][peer]);
+    const uint32_t ack = ld_relaxed_sys(&sb.ack[ch][peer]);
     if (ro.pushes_to(t)) {
-      const uint32_t v = sb.sent[ch][peer] + 1;
+      const uint32_t v = sent + 1;
       // the staging region of parity v & 1 was last used by message v - 2: it must have been consumed
-      if (v > 2) wait_ge(&sb.ack[ch][peer], v - 2, c, DEQUEUE_BUFFER_TIMEOUT_ERROR);
+      if (v > 2 && static_cast<int32_t>(ack - (v - 2)) < 0) wait_ge(&sb.ack[ch][peer], v - 2, c, DEQUEUE_BUFFER_TIMEOUT_ERROR);
       s_v[t] = v;
       sb.sent[ch][peer] = v;
     }
     if (ro.expects_from(t)) {
-      const uint32_t e = sb.recvd[ch][peer] + 1;
+      const uint32_t e = recvd + 1;
       s_e[t] = e;
       sb.recvd[ch][peer] = e;
     }
@@ -250,11 +254,14 @@ __device__ __noinline__ void ll_exchange(const Ctx &c, StgPattern pat, const cha
     if (threadIdx.x == 0) atomicOr(c.err, DMA_SIZE_ERROR);
     return;
   }
+  // the first line of a same-source push does not depend on the counters: its load overlaps their round trip
+  const bool same = ro.same_src();
+  uint2 first{0, 0};
+  if (same && threadIdx.x < lines) first = ld8_local(src, part.off + static_cast<size_t>(threadIdx.x) * 8, blk);
   stg_open(c, ro, s_v, s_e);
   // ---- push
-  const bool same = ro.same_src();
   for (size_t i = threadIdx.x; i < lines; i += blockDim.x) {
-    uint2 v = same ? ld8_local(src, part.off + i * 8, blk) : uint2{0, 0};
+    uint2 v = same ? (i == threadIdx.x ? first : ld8_local(src, part.off + i * 8, blk)) : uint2{0, 0};
     for (uint32_t k = 1; k < P; ++k) {
       const uint32_t q = (me + k) % P; // stagger destinations across ranks
       const uint32_t sv = s_v[q];

@@ -31,25 +31,29 @@ def test_one_way_protocol_selection():
     p = plan(Op.allreduce, 1024)
     assert p["algo"] == "ll" and p["oneshot"] and p["n_ctas"] == 1
     p = plan(Op.allreduce, 64 << 10)
-    assert p["algo"] == "ll" and not p["oneshot"]                     # shards of 8 KiB <= ll_max_bytes
-    p = plan(Op.allreduce, 2 << 20, max_eager_bytes=4 << 20)
-    assert p["algo"] == "staged" and not p["oneshot"]                 # shards of 256 KiB: payload + release flag
+    assert p["algo"] == "ll" and not p["oneshot"]                     # shards of 8 KiB through the flag-in-data protocol
+    p = plan(Op.allreduce, 2 << 20, max_eager_bytes=4 << 20, ll_kb=2048)
+    assert p["algo"] == "ll" and not p["oneshot"] and p["n_ctas"] == 32   # shards of 256 KiB: 32 K lines over all channels
+    # what does not fit the LL region goes to the slot ring, or to the payload + flag protocol when that is enabled
+    assert plan(Op.allreduce, 2 << 20, max_eager_bytes=4 << 20)["algo"] == "eager"
+    assert plan(Op.allreduce, 2 << 20, max_eager_bytes=4 << 20, staged_max_bytes=1 << 20)["algo"] == "staged"
     # sizes that do not split into 16-byte shards go one-shot while small, to the slot ring otherwise
     assert plan(Op.allreduce, 20000)["oneshot"]
     assert plan(Op.allreduce, (1 << 20) + 4, max_eager_bytes=4 << 20)["algo"] == "eager"
     # per-peer message decides for the others
     assert plan(Op.allgather, 8 << 10)["algo"] == "ll"
-    assert plan(Op.allgather, 256 << 10, max_eager_bytes=1 << 20)["algo"] == "staged"
     assert plan(Op.reduce_scatter, 16 << 10)["algo"] == "ll"
-    assert plan(Op.bcast, 32 << 10)["algo"] == "staged"
-    # a message that does not fit the staging region falls back to the slot ring
-    assert plan(Op.allgather, 2 << 20, max_eager_bytes=4 << 20)["algo"] == "eager"
-    assert plan(Op.allgather, 2 << 20, max_eager_bytes=4 << 20, stage_kb=4096)["algo"] == "staged"
+    assert plan(Op.bcast, 32 << 10)["algo"] == "ll"
+    assert plan(Op.bcast, 32 << 10, ll_max_bytes=16384, staged_max_bytes=1 << 20)["algo"] == "staged"   # the crossover is a knob
+    assert plan(Op.allgather, 256 << 10, max_eager_bytes=1 << 20, staged_max_bytes=1 << 20)["algo"] == "staged"   # 256 KiB > LL capacity of 128 KiB
+    assert plan(Op.allgather, 256 << 10, max_eager_bytes=1 << 20, ll_kb=2048)["algo"] == "ll"
     # no staging configured: everything one-way is the slot ring
     assert plan(Op.allreduce, 1024, stage_kb=0, ll_kb=0)["algo"] == "eager"
     # channel counts: every channel owns 1/32 of a region
-    assert plan(Op.allgather, 256 << 10, max_eager_bytes=1 << 20)["n_ctas"] == 8   # 32 KiB per channel
-    assert plan(Op.allgather, 1 << 20, max_eager_bytes=1 << 20)["n_ctas"] == 32
+    assert plan(Op.allgather, 256 << 10, max_eager_bytes=1 << 20, staged_max_bytes=1 << 20)["n_ctas"] == 8   # 32 KiB per channel
+    # inside the engine a message that fits one channel stays on one (executed inline by the control CTA)
+    assert plan(Op.allreduce, 8 << 10, ll_kb=2048, engine_mode=True)["n_ctas"] == 1
+    assert plan(Op.allreduce, 8 << 10, ll_kb=2048)["n_ctas"] == 2
 
 
 def test_allreduce_algorithm_by_size_and_world():
