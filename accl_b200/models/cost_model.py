@@ -20,25 +20,26 @@ from dataclasses import dataclass
 class Fabric:
     bw_GBps: float = 900.0       # NVLink 5, per direction per GPU (nominal)
     bw_measured_GBps: float = 770.0  # peer copy measured on this pool (B200_PROFILING.md)
-    alpha_us: float = 2.5        # one flag round trip between GPUs (measured: ~2.4-2.8 us)
+    alpha_us: float = 1.5        # one-way flag / data latency between GPUs over the switch (LL exchange: ~1.2-1.8 us)
     launch_us: float = 4.0       # kernel launch + completion on the issuing stream
 
 
-def ideal_us(op: str, nbytes: int, world: int, fabric: Fabric = Fabric(), nvls: bool = True, measured: bool = True) -> float:
-    """Ideal device time of one call in microseconds."""
+def ideal_us(op: str, nbytes: int, world: int, fabric: Fabric = Fabric(), nvls: bool = True, measured: bool = False) -> float:
+    """Ideal device time of one call in microseconds.  Graded against the nominal 900 GB/s per direction per GPU that
+    BASELINE.json names (measured=True switches to the 770 GB/s peer-copy rate measured on this pool)."""
     if world == 1:
         return nbytes / 6.5e6  # local copy at HBM rate (read+write), bytes / (6.5 TB/s / 2 ... ) kept simple
     bw = (fabric.bw_measured_GBps if measured else fabric.bw_GBps) * 1e3  # bytes per microsecond
     p = world
     if op == "allreduce":
         link_bytes = nbytes * (1 + 1 / p) if nvls and p >= 3 else 2 * nbytes * (p - 1) / p
-        syncs = 2
+        syncs = 2  # two hops (reduce-scatter + all-gather)
     elif op in ("allgather", "reduce_scatter", "alltoall", "scatter", "gather"):
         link_bytes = nbytes * (p - 1) / p
-        syncs = 2
+        syncs = 1  # one hop
     elif op in ("bcast", "reduce", "sendrecv"):
         link_bytes = nbytes
-        syncs = 2
+        syncs = 1
     elif op == "barrier":
         link_bytes, syncs = 0, 1
     else:

@@ -1,1 +1,1 @@
-from .plugins import gemm_reduce_scatter, stream_loopback, vadd_allreduce  # noqa: F401
+from .plugins import gemm_reduce_scatter, stream_loopback, stream_pull, vadd_allreduce, vadd_put  # noqa: F401

@@ -39,6 +39,8 @@ def init_from_env(backend=None, **kw):
     init_kw = {k: kw.pop(k) for k in list(kw) if k in init_keys}
     if backend == "cuda":
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        if "engine" not in kw and os.environ.get("ACCL_PG_ENGINE") is not None:
+            kw["engine"] = os.environ["ACCL_PG_ENGINE"] not in ("", "0")
         acc = cuda_rank(**kw)
         init_kw.setdefault("n_egr_rx_bufs", 4)
         init_kw.setdefault("egr_rx_buf_size", 64 << 10)
@@ -64,6 +66,35 @@ class TensorGroup:
         # buffer is its host mirror, so calls are blocking and sync to / from the engine's memory themselves.
         self._res = bool(accl.is_cuda)
         self._async = bool(accl.is_cuda)
+        # engine mode: asynchronous point-to-point calls do not hold the stream (they may stay parked until the peer posts
+        # its side), so a staged receive has to be waited for on the host before its staging buffer is read
+        self._engine = bool(accl.is_cuda) and "mode=engine" in accl.describe()
+        self._pending = []  # asynchronous requests whose return code has not been looked at yet
+
+    # -- request bookkeeping ---------------------------------------------------
+    def _track(self, req):
+        """Keep an asynchronous request until it has completed, then check its return code: a device-side timeout,
+        tag mismatch or protocol error must not go unnoticed while training continues on garbage."""
+        if req is None or not hasattr(req, "test"):
+            return req
+        self._pending.append(req)
+        self.check(block=len(self._pending) > 64)
+        return req
+
+    def check(self, block=False):
+        """Raise if any finished call reported an error; with block=True wait for everything outstanding."""
+        keep = []
+        for r in self._pending:
+            if block:
+                r.wait()
+            if block or r.test():
+                rc = r.retcode()
+                if rc:
+                    self._pending = [q for q in self._pending if q is not r]
+                    raise RuntimeError(f"accl call failed on rank {self.rank}: {_C.error_to_string(rc)} (0x{rc:x})")
+            else:
+                keep.append(r)
+        self._pending = keep
 
     def _t(self, buf):
         """The torch tensor aliasing a buffer on this backend."""
@@ -95,9 +126,9 @@ class TensorGroup:
         db, d_staged = (sb, s_staged) if dst is src else self._buffer_of(dst, "d")
         if s_staged:
             self._t(sb)[:src.numel()].copy_(src.reshape(-1))
-        req = fn(sb, db)
+        req = self._track(fn(sb, db))
         if d_staged:
-            dst.reshape(-1).copy_(self._t(db)[:dst.numel()])
+            dst.copy_(self._t(db)[:dst.numel()].view_as(dst))  # (works for non-contiguous destinations too)
         return req
 
     # -- collectives ---------------------------------------------------------
@@ -126,17 +157,20 @@ class TensorGroup:
         if staged:
             self._t(sb)[:t.numel()].copy_(t.reshape(-1))
         # always asynchronous: a blocking rendezvous send would wait for the peer's recv
-        return self.accl.send(sb, t.numel(), dst, tag, self.comm_id, self._res, run_async=True)
+        return self._track(self.accl.send(sb, t.numel(), dst, tag, self.comm_id, self._res, run_async=True))
 
     def recv(self, t: torch.Tensor, src, tag=0):
         db, staged = self._buffer_of(t, "d")
-        req = self.accl.recv(db, t.numel(), src, tag, self.comm_id, self._res, run_async=self._async)
+        req = self._track(self.accl.recv(db, t.numel(), src, tag, self.comm_id, self._res, run_async=self._async))
         if staged:
-            t.reshape(-1).copy_(self._t(db)[:t.numel()])
+            if self._engine and req is not None:
+                req.wait()
+            t.copy_(self._t(db)[:t.numel()].view_as(t))
         return req
 
     def barrier(self):
         self.accl.barrier(self.comm_id)
+        self.check(block=True)
 
 
 class GradBucket:
@@ -171,7 +205,7 @@ class GradBucket:
         n = self.numel // self.group.world
         out = self.group.empty(n, dtype=self.flat.dtype)
         g = self.group
-        g.accl.reduce_scatter(buf, out._accl_buffer, n, SUM, g.comm_id, g._res, g._res, run_async=g._async)
+        g._track(g.accl.reduce_scatter(buf, out._accl_buffer, n, SUM, g.comm_id, g._res, g._res, run_async=g._async))
         del shard
         return out
 

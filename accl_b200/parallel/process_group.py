@@ -30,11 +30,11 @@ def _done(result):
 
 
 class AcclProcessGroup(dist.ProcessGroup):
-    def __init__(self, rank, world_size, accl):
+    def __init__(self, rank, world_size, accl, comm_id=0):
         super().__init__(rank, world_size)
         self._rank, self._world = rank, world_size
         self.accl = accl
-        self.group = TensorGroup(accl)
+        self.group = TensorGroup(accl, comm_id)
 
     # -- identity ------------------------------------------------------------
     def getBackendName(self):
@@ -86,8 +86,8 @@ class AcclProcessGroup(dist.ProcessGroup):
             sb, _ = self.group._buffer_of(flat, "s")
             db, _ = self.group._buffer_of(flat, "d")
             self.group._t(sb)[:n].copy_(flat)
-            self.accl.reduce(sb, db, n, opts.rootRank, fn, self.group.comm_id, self.group._res, self.group._res,
-                             run_async=self.group._async)
+            self.group._track(self.accl.reduce(sb, db, n, opts.rootRank, fn, self.group.comm_id, self.group._res,
+                                               self.group._res, run_async=self.group._async))
             if self._rank == opts.rootRank:
                 t.copy_(self.group._t(db)[:n].view_as(t))
                 self._finish(t, post)
@@ -146,8 +146,8 @@ class AcclProcessGroup(dist.ProcessGroup):
         sb, _ = self.group._buffer_of(inp.view(-1), "s")
         db = self.accl.create_buffer(n * self._world, inp.dtype)
         self.group._t(sb)[:n].copy_(inp.view(-1))
-        self.accl.gather(sb, db, n, opts.rootRank, self.group.comm_id, self.group._res, self.group._res,
-                         run_async=self.group._async)
+        self.group._track(self.accl.gather(sb, db, n, opts.rootRank, self.group.comm_id, self.group._res, self.group._res,
+                                           run_async=self.group._async))
         if self._rank == opts.rootRank:
             for o, chunk in zip(output_tensors[0], self.group._t(db).chunk(self._world)):
                 o.copy_(chunk.view_as(o))
@@ -160,8 +160,8 @@ class AcclProcessGroup(dist.ProcessGroup):
         db, _ = self.group._buffer_of(out.reshape(-1), "d")
         if self._rank == opts.rootRank:
             self.group._t(sb).copy_(torch.cat([t.reshape(-1) for t in input_tensors[0]]))
-        self.accl.scatter(sb, db, n, opts.rootRank, self.group.comm_id, self.group._res, self.group._res,
-                          run_async=self.group._async)
+        self.group._track(self.accl.scatter(sb, db, n, opts.rootRank, self.group.comm_id, self.group._res, self.group._res,
+                                            run_async=self.group._async))
         out.copy_(self.group._t(db)[:n].view_as(out))
         return _done(output_tensors)
 
@@ -182,12 +182,42 @@ class AcclProcessGroup(dist.ProcessGroup):
         return _done(tensors)
 
 
-def _create(store, rank, world_size, timeout):
-    os.environ.setdefault("RANK", str(rank))
-    os.environ.setdefault("WORLD_SIZE", str(world_size))
-    accl = init_from_env(None)
-    assert accl.rank == rank and accl.world == world_size, "accl backend: RANK / WORLD_SIZE disagree with init_process_group"
-    return AcclProcessGroup(rank, world_size, accl)
+_primary = {}  # the world-sized engine of this process: sub-groups are communicators on it
 
 
-dist.Backend.register_backend("accl", _create, devices=["cpu", "cuda"])
+def _create(opts, pg_options=None):
+    """Backend constructor (extended API).  The default group builds the engine: ranks meet over a private TCP
+    rendezvous whose port is published through the store that torch.distributed hands us (so `init_method` /
+    the store decide, not only the environment).  Every further group (`dist.new_group(ranks)`) becomes a
+    communicator on that engine (accl::ACCL::create_communicator) with its own protocol-state bank."""
+    store, rank, size = opts.store, opts.group_rank, opts.group_size
+    ranks = list(getattr(opts, "global_ranks_in_group", []) or range(size))
+    if "accl" not in _primary:
+        if ranks != list(range(size)):
+            raise NotImplementedError("accl backend: the first process group must span all ranks (default group)")
+        os.environ["RANK"] = str(rank)
+        os.environ["WORLD_SIZE"] = str(size)
+        # publish / fetch the bootstrap port through the store (rank 0 derives it from MASTER_PORT or picks 29637)
+        if rank == 0:
+            port = int(os.environ.get("ACCL_PORT", int(os.environ.get("MASTER_PORT", 29500)) + 137))
+            store.set("accl_bootstrap_port", str(port))
+        port = int(store.get("accl_bootstrap_port").decode())
+        os.environ["ACCL_PORT"] = str(port)
+        os.environ["ACCL_EMU_PORT"] = str(port)
+        accl = init_from_env(None)
+        assert accl.rank == rank and accl.world == size, "accl backend: rank / world size disagree with init_process_group"
+        _primary["accl"] = accl
+        _primary["ranks"] = accl.generate_ranks(size)
+        return AcclProcessGroup(rank, size, accl)
+    accl = _primary["accl"]
+    if ranks == list(range(accl.world)):
+        # another world-sized group: its own communicator (and bank) so it can be used concurrently
+        comm = accl.create_communicator(list(_primary["ranks"]), accl.rank)
+        return AcclProcessGroup(rank, size, accl, comm)
+    if accl.rank not in ranks:
+        raise NotImplementedError("accl backend: this rank is not a member of the group being created")
+    comm = accl.create_communicator([_primary["ranks"][g] for g in ranks], ranks.index(accl.rank))
+    return AcclProcessGroup(ranks.index(accl.rank), len(ranks), accl, comm)
+
+
+dist.Backend.register_backend("accl", _create, extended_api=True, devices=["cpu", "cuda"])

@@ -46,11 +46,10 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(11 + rank)
     s.dev.copy_((torch.rand(n, device="cuda", generator=g) * 2 - 1).to(dt))
     probe = slice(n // 3, n // 3 + (1 << 20))
-    ref = s.dev[probe].double()
-    if args.what == "allreduce" or args.what == "reduce":
-        dist.all_reduce(ref)
-    else:
-        dist.broadcast(ref, 0)
+    ref_sum = s.dev[probe].double()
+    dist.all_reduce(ref_sum)
+    ref_b = s.dev[probe].double()
+    dist.broadcast(ref_b, 0)
     kw = dict(from_fpga=True, to_fpga=True, run_async=True)
     tol = {torch.float32: 1e-4, torch.bfloat16: 0.15, torch.float16: 0.03}[dt]
 
@@ -82,7 +81,9 @@ def main():
                 fh.write(json.dumps(row) + "\n")
                 fh.flush()
 
-    if args.what == "allreduce":
+    whats = args.what.split(",")
+    if "allreduce" in whats:
+        ref = ref_sum
         ctas = [32, 64, 96, 128] if args.quick else [32, 48, 64, 80, 96, 128]
         unroll = [8, 16] if args.quick else [4, 8, 16]
         hyb = [0, 3] if args.quick else [0, 1, 2, 3, 4, 6]
@@ -95,9 +96,14 @@ def main():
             err = float((d.dev[probe].double() - ref).abs().max())
             emit(dict(what="allreduce", mb=args.mb, dtype=args.dtype, world=world, nvls_ctas=c, nvls_unroll=u, hybrid_16ths=h,
                       us=ms * 1e3, busbw=nbytes / ms * 1e-6 * f, ok=err <= tol * world, err=err))
-        ms = timed(lambda: dist.all_reduce(s.dev))  # destroys s: last
+        x = s.dev.clone()
+        ms = timed(lambda: dist.all_reduce(x))
+        del x
         emit(dict(what="allreduce", mb=args.mb, dtype=args.dtype, world=world, impl="nccl", us=ms * 1e3, busbw=nbytes / ms * 1e-6 * f))
-    elif args.what == "reduce":
+        for k, v in (("nvls_ctas", 64), ("nvls_unroll", 8), ("hybrid_16ths", 0)):
+            acc.set_tuning(k, v)
+    if "reduce" in whats:
+        ref = ref_sum
         for push, c in itertools.product([0, 1], [64, 128]):
             acc.set_tuning("reduce_push", push)
             acc.set_tuning("max_ctas", c)
@@ -108,13 +114,17 @@ def main():
                       busbw=nbytes / ms * 1e-6, ok=err <= tol * world, err=err))
         x = s.dev.clone()
         ms = timed(lambda: dist.reduce(x, 0))
+        del x
         emit(dict(what="reduce", mb=args.mb, dtype=args.dtype, world=world, impl="nccl", us=ms * 1e3, busbw=nbytes / ms * 1e-6))
-    elif args.what == "bcast":
+        acc.set_tuning("reduce_push", 0)
+        acc.set_tuning("max_ctas", 128)
+    if "bcast" in whats:
+        ref = ref_b
         for fl, c in itertools.product([0, 1], [64, 128]):
             acc.set_tuning("bcast_flags", fl)
             acc.set_tuning("max_ctas", c)
             if rank != 0:
-                s.dev.zero_()
+                s.dev[probe].zero_()
             torch.cuda.synchronize()
             dist.barrier()
             ms = timed(lambda: acc.bcast(s, n, 0, **kw).free())

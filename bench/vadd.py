@@ -3,10 +3,11 @@ through the device API, vs the unfused baseline (torch add kernel + NCCL all_red
 
   python -m torch.distributed.run --nproc-per-node N ... bench/vadd.py [--min-log2 12 --max-log2 26]
 
-Fused: one `k_plugin_vadd_allreduce` launch per step; its last CTA takes a ticket in the resident engine's
-device ring (`accl::device::Command::all_reduce`), the control CTA plans the call and the worker CTAs run it —
-no host on the path after the launch.  Device-timed with CUDA events, max over ranks.  Note: the engine
-mode needs `CUDA_DEVICE_MAX_CONNECTIONS >= 2`; the launcher sets 32.
+Fused: one `k_plugin_vadd_allreduce` launch per step.  The kernel produces x + y chunk by chunk; the CTA that
+completes a chunk takes a ticket in the resident engine's command ring (`accl::device::Command::all_reduce_async`)
+and the kernel goes on computing while the engine's control CTA plans the call and its worker CTAs reduce the
+chunk over NVLink — no host on the path after the launch, compute and communication overlap.  Device-timed with
+CUDA events, max over ranks.  Note: the engine mode needs `CUDA_DEVICE_MAX_CONNECTIONS >= 2`; the launcher sets 32.
 """
 import argparse
 import json
@@ -28,6 +29,8 @@ def main():
     ap.add_argument("--step", type=int, default=2)
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--max-ctas", type=int, default=64)
+    ap.add_argument("--engine-workers", type=int, default=48)
+    ap.add_argument("--chunk-kb", type=int, default=4096, help="bytes of x + y handed to the engine per device-issued all-reduce")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -35,8 +38,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nmax = (1 << a.max_log2) // 4
-    acc = A.cuda_rank(rank, world, local, heap_mb=max(512, (16 * nmax >> 20) + 256), max_ctas=a.max_ctas, engine=True)
-    acc.initialize(n_egr_rx_bufs=4, egr_rx_buf_size=64 << 10, max_egr_size=64 << 10, max_rndzv_size=1 << 30)
+    acc = A.cuda_rank(rank, world, local, heap_mb=max(768, (16 * nmax >> 20) + 512), max_ctas=a.max_ctas, engine=True,
+                      engine_workers=a.engine_workers)
+    acc.initialize(n_egr_rx_bufs=4, egr_rx_buf_size=64 << 10, max_egr_size=1 << 20, max_rndzv_size=1 << 30)
+    if rank == 0:
+        print("#", acc.describe(), flush=True)
     x, y, tmp, out = (acc.create_buffer(nmax, torch.float32) for _ in range(4))
     x.dev.fill_(1.0)
     y.dev.fill_(float(rank))
@@ -68,7 +74,7 @@ def main():
         statuses = []
 
         def fused():
-            statuses.append(vadd_allreduce(acc, x, y, out, tmp, n))
+            statuses.append(vadd_allreduce(acc, x, y, out, tmp, n, chunk_elems=(a.chunk_kb << 10) // 4))
             if len(statuses) > 8:
                 statuses.pop(0)
 
@@ -81,8 +87,7 @@ def main():
         fused()
         torch.cuda.synchronize()
         expect = float(world + sum(range(world)))
-        got = out.dev[:min(n, 64)].float().cpu()
-        ok = bool(torch.all(got == expect)) and int(statuses[-1].item()) == 0
+        ok = bool(torch.all(out.dev[:n] == expect)) and int(statuses[-1].item()) == 0
         iters = a.iters if lg <= 22 else max(5, a.iters // 5)
         ms_f = timed(fused, iters)
         ms_b = timed(baseline, iters)

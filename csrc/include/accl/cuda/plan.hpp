@@ -103,15 +103,16 @@ ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
   const bool compressed = w.desc.compression_flags != 0;
   const bool p2p = op == operation::send || op == operation::recv;
   const bool eager = compressed || ubytes <= exch[exchmem::MAX_EAGER_SIZE / 4];
+  bool eager_ok = eager;
   if (eager && !compressed && !p2p && ubytes && cfg.ll_bytes) {
-    // one-way staged exchange: flag-in-data (LL) while latency dominates, payload + release flag above
+    // one-way staged exchange: flag-in-data (LL) while it fits, payload + release flag when enabled
     uint64_t m = ubytes;
     uint32_t extra = 0;
     bool ok = true;
     if (op == operation::allreduce) {
       if (ubytes <= cfg.ll_oneshot_max || ubytes % (16ull * P) != 0) extra = WF_ONESHOT; // everybody receives everything
       else m = ubytes / P;                                                               // shards: reduce-scatter + all-gather
-      // a one-shot of a large odd-sized message would move P x the bytes: leave it to the slot path
+      // a one-shot of a large odd-sized message would move P x the bytes: leave it to the other paths
       if ((extra & WF_ONESHOT) && ubytes > 4ull * cfg.ll_oneshot_max && ubytes > (256u << 10)) ok = false;
     }
     if (ok) {
@@ -128,6 +129,10 @@ ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
         return;
       }
     }
+    // does not fit the staging regions: segment after segment through the slot ring only while that is a handful of
+    // segments, else the rendezvous algorithms (measured: 4 MiB all-gather on 2 GPUs 45 us through the slots, 17 us
+    // between user buffers)
+    if (ubytes > 8ull * exch[exchmem::EAGER_RX_BUF_SIZE / 4]) eager_ok = false;
   }
   // compressed wire, uncompressed operands, large message: the cast is fused into the two-shot exchange
   // (compress.cuh) instead of pushing segment after segment through the slot ring
@@ -143,7 +148,7 @@ ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
       return;
     }
   }
-  if (eager) {
+  if (eager_ok) {
     w.algo = ALGO_EAGER;
     const uint32_t ecap = cap < static_cast<uint32_t>(EGR_CH) ? cap : static_cast<uint32_t>(EGR_CH);
     w.n_ctas = p2p ? 1 : plan_ctas(ubytes, 16u << 10, ecap);

@@ -179,6 +179,7 @@ private:
 
   struct Ctx; // decoded call context (engine.cpp)
   bool decode(EmuCall &c, Ctx &x, uint32_t &err);
+  void purge_notes_of(EmuCall &c);
 
   // eager building blocks (blocking, like the DMP)
   uint32_t egr_send(Ctx &x, uint32_t dst, Operand src, uint32_t count, uint32_t tag, bool to_stream, uint32_t strm);

@@ -26,7 +26,8 @@ enum class MsgType : uint32_t {
   EGR_MSG = 0,        // eager payload, lands in a spare RX buffer (or a stream when strm != 0)
   RNDZVS_MSG = 1,     // one-sided write of payload to `vaddr`
   RNDZVS_INIT = 2,    // receiver -> sender: "my buffer for (tag) is at vaddr"
-  RNDZVS_WR_DONE = 3  // sender -> receiver: the write for (tag) has completed
+  RNDZVS_WR_DONE = 3, // sender -> receiver: the write for (tag) has completed
+  RNDZVS_CANCEL = 4   // receiver -> sender: forget my address note for (tag, vaddr) — the recv that posted it timed out
 };
 
 struct MsgHeader {

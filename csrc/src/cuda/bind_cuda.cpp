@@ -60,6 +60,7 @@ void bind_cuda(py::module_ &m) {
                         uint32_t ll_kb, uint32_t ll_max_bytes, uint32_t ll_oneshot_max, uint32_t staged_max_bytes, bool engine_mode) {
     std::vector<uint32_t> exch(exchmem::SIZE_WORDS, 0);
     exch[exchmem::MAX_EAGER_SIZE / 4] = max_eager_bytes;
+    exch[exchmem::EAGER_RX_BUF_SIZE / 4] = 64u << 10;
     PlanCfg cfg{};
     cfg.max_ctas = max_ctas;
     cfg.nvls_min_ranks = nvls_min_ranks;

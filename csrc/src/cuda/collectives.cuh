@@ -911,7 +911,7 @@ __device__ __noinline__ void rv_send(const Ctx &c, uint64_t *s_pair) {
   }
   __shared__ uint64_t s_o;
   __shared__ uint32_t s_k;
-  pair_sync(c, it.desc.root_src_dst, 0, static_cast<uint32_t>(operation::send), &s_o, &s_k);
+  pair_sync(c, it.desc.root_src_dst, 0, static_cast<uint32_t>(operation::send), &s_o, &s_k, false);
 }
 
 __device__ __noinline__ void rv_recv(const Ctx &c, uint64_t *s_pair) {
@@ -922,7 +922,7 @@ __device__ __noinline__ void rv_recv(const Ctx &c, uint64_t *s_pair) {
     atomicOr(c.err, PACK_SEQ_NUMBER_ERROR);
   __shared__ uint64_t s_o;
   __shared__ uint32_t s_k;
-  pair_sync(c, it.desc.root_src_dst, 0, static_cast<uint32_t>(operation::recv), &s_o, &s_k);
+  pair_sync(c, it.desc.root_src_dst, 0, static_cast<uint32_t>(operation::recv), &s_o, &s_k, false);
 }
 
 } // namespace k

@@ -641,9 +641,14 @@ __global__ void __launch_bounds__(32) k_submit(DevWorld w, WorkItem item, int wa
   Ctrl *me = my_ctrl(w);
   EngineArea *ea = engine_area(w);
   unsigned long long t = 0;
+  const unsigned long long budget_ns = static_cast<unsigned long long>(item.timeout_us) * 1000ull;
   if (threadIdx.x == 0) {
     t = atomicAdd(&me->cmd_tail, 1ull);
-    while (t >= dev::ld_acquire_sys(&me->cmd_fetched) + RING_SLOTS) dev::nanosleep(100); // ring full
+    const unsigned long long t0 = dev::globaltimer_ns();
+    while (t >= dev::ld_acquire_sys(&me->cmd_fetched) + RING_SLOTS) { // ring full
+      dev::nanosleep(100);
+      if (dev::globaltimer_ns() - t0 > budget_ns) break; // no engine is consuming (a tool serialising kernels?): give up
+    }
   }
   t = __shfl_sync(0xffffffffu, t, 0);
   const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&item);
@@ -655,10 +660,15 @@ __global__ void __launch_bounds__(32) k_submit(DevWorld w, WorkItem item, int wa
     dev::st_release_sys(&me->cmd_ready[t % RING_SLOTS], t + 1);
     if (wait_done) {
       const unsigned long long *st = &me->cmd_status[t % RING_SLOTS];
+      const unsigned long long t0 = dev::globaltimer_ns();
       uint32_t spins = 0;
       // (>=: a later occupant of the slot may have retired already if 128 calls overtook a parked one)
-      while (static_cast<int32_t>(static_cast<uint32_t>(dev::ld_acquire_sys(st)) - static_cast<uint32_t>(t + 1)) < 0)
+      while (static_cast<int32_t>(static_cast<uint32_t>(dev::ld_acquire_sys(st)) - static_cast<uint32_t>(t + 1)) < 0) {
         if (++spins > 64) dev::nanosleep(spins > 1024 ? 200 : 20);
+        // the engine retires a call within its wait budget (parked calls time out there); twice that without an
+        // answer means no engine is running next to this proxy
+        if ((spins & 0x3FF) == 0 && dev::globaltimer_ns() - t0 > 2 * budget_ns + 1000000ull) break;
+      }
     }
   }
 }

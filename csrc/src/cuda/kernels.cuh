@@ -112,8 +112,10 @@ __device__ __forceinline__ void chan_sync(const Ctx &c, bool exchange, uint64_t 
 }
 
 // pairwise variant for send/recv in direct mode: only (me, peer) take part; kinds differ by design
+// `post_rec` = false: signal only.  The second meeting of a transfer must NOT rewrite the record: the peer may not have
+// read the first one yet (the receiver runs straight from its first into its second meeting).
 __device__ __forceinline__ void pair_sync(const Ctx &c, uint32_t peer_comm_rank, uint64_t my_off, uint32_t my_kind,
-                                          uint64_t *peer_off, uint32_t *peer_kind) {
+                                          uint64_t *peer_off, uint32_t *peer_kind, bool post_rec = true) {
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t ch = static_cast<uint32_t>(c.cta);
@@ -122,9 +124,11 @@ __device__ __forceinline__ void pair_sync(const Ctx &c, uint32_t peer_comm_rank,
     PadBank &theirs = c.pads_of(peer);
     const uint32_t v = mine.sent[ch][peer] + 1;
     mine.sent[ch][peer] = v;
-    SyncRec *rr = &theirs.rec[ch][c.w.rank];
-    st_relaxed_sys(&rr->off0, my_off);
-    st_relaxed_sys(&rr->kind, my_kind);
+    if (post_rec) {
+      SyncRec *rr = &theirs.rec[ch][c.w.rank];
+      st_relaxed_sys(&rr->off0, my_off);
+      st_relaxed_sys(&rr->kind, my_kind);
+    }
     st_release_sys(&theirs.sig[ch][c.w.rank], v);
     const uint32_t e = mine.expect[ch][peer] + 1;
     mine.expect[ch][peer] = e;

@@ -335,33 +335,50 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  // ---------------- zero my output shard (all threads of all CTAs), then meet the peers
-  {
+  // ---------------- zero my output shard and meet the peers — WITHOUT holding back the math: the TMA producer
+  // (warp 0) and the MMA issuer (warp 1) go straight to the main loop; warps 2-7 zero the shard (the reduce-adds
+  // accumulate into it), warp 3 of CTA 0 then exchanges the shard offsets with the peers on the sync pads and
+  // releases the epilogues of the whole grid.  The first tile's accumulator is ready long after (K / 64 x 512 cycles).
+  k::Ctx ctx{p.w, s_item, MAX_CH - 1, 1, reinterpret_cast<Ctrl *>(my_heap), &s_err, static_cast<uint64_t>(p.timeout_us) * 1000ull, &s_tab};
+  if (warp >= 2) {
     dev::Vec16 z{0, 0, 0, 0};
     char *shard = my_heap + p.out_off;
     const size_t nvec = static_cast<size_t>(rows_per_rank) * p.n * (F32 ? 4 : 2) / 16;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-      dev::st_stream(shard + i * 16, z);
+    const size_t zt = static_cast<size_t>(blockIdx.x) * 192 + (threadIdx.x - 64), zstride = static_cast<size_t>(gridDim.x) * 192;
+    for (size_t i = zt; i < nvec; i += zstride) dev::st_stream(shard + i * 16, z);
     __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(&p.grid_flags[0], 1u);
-  }
-  if (blockIdx.x == 0 && warp == 3) {
-    // the whole grid has zeroed -> exchange shard offsets with every peer (sync pads, channel MAX_CH-1)
-    if (lane == 0)
-      while (atomicAdd(&p.grid_flags[0], 0u) < gridDim.x) dev::nanosleep(100);
-    __syncwarp();
-    __threadfence();
-  }
-  // (the barrier itself is executed by all threads of CTA 0 below; other CTAs go straight to work)
-  k::Ctx ctx{p.w, s_item, MAX_CH - 1, 1, reinterpret_cast<Ctrl *>(my_heap), &s_err, static_cast<uint64_t>(p.timeout_us) * 1000ull, &s_tab};
-  if (blockIdx.x == 0) {
-    __syncthreads();
-    k::chan_sync(ctx, true, p.out_off, p.out_off, s_off0, s_off2);
-    if (threadIdx.x < P) reinterpret_cast<volatile uint64_t *>(p.grid_flags + 8)[threadIdx.x] = s_off0[threadIdx.x];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicExch(&p.grid_flags[1], 1u); // release the epilogues of every CTA
+    asm volatile("bar.sync 1, 192;" ::: "memory"); // warps 2-7 only
+    if (threadIdx.x == 64) atomicAdd(&p.grid_flags[0], 1u);
+    if (blockIdx.x == 0 && warp == 3) {
+      // the whole grid has zeroed -> meet every peer (sync pads, channel MAX_CH-1), one lane per peer
+      if (lane == 0)
+        while (atomicAdd(&p.grid_flags[0], 0u) < gridDim.x) dev::nanosleep(100);
+      __syncwarp();
+      __threadfence();
+      uint64_t peer_off = p.out_off;
+      if (static_cast<uint32_t>(lane) < P && static_cast<uint32_t>(lane) != me) {
+        PadBank &mine = ctx.pads();
+        PadBank &theirs = ctx.pads_of(lane);
+        const uint32_t ch = MAX_CH - 1;
+        const uint32_t v = mine.sent[ch][lane] + 1;
+        mine.sent[ch][lane] = v;
+        SyncRec *rr = &theirs.rec[ch][me];
+        dev::st_relaxed_sys(&rr->off0, p.out_off);
+        dev::st_relaxed_sys(&rr->off2, p.out_off);
+        dev::st_relaxed_sys(&rr->kind, ctx.kind_word());
+        dev::st_release_sys(&theirs.sig[ch][me], v);
+        const uint32_t e = mine.expect[ch][lane] + 1;
+        mine.expect[ch][lane] = e;
+        if (k::wait_ge(&mine.sig[ch][lane], e, ctx, RECEIVE_TIMEOUT_ERROR)) {
+          peer_off = dev::ld_relaxed_sys(&mine.rec[ch][lane].off0);
+          if (dev::ld_relaxed_sys(&mine.rec[ch][lane].kind) != ctx.kind_word()) atomicOr(&s_err, PACK_SEQ_NUMBER_ERROR);
+        }
+      }
+      if (static_cast<uint32_t>(lane) < P) reinterpret_cast<volatile uint64_t *>(p.grid_flags + 8)[lane] = peer_off;
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicExch(&p.grid_flags[1], 1u); // release the epilogues of every CTA
+    }
   }
 
   // ---------------- warp-specialised main loop

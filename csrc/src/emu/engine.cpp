@@ -194,6 +194,7 @@ void Engine::control_loop() {
       const uint64_t waited_us = (now_ns() - c.t0_ns) / 1000;
       if (waited_us > std::max<uint64_t>(60ull * 1000000ull, 2ull * timeout_us())) {
         rc = RECEIVE_TIMEOUT_ERROR;
+        purge_notes_of(c); // what it posted to peers / what peers addressed to it must not be matched by a later call
       } else {
         std::lock_guard<std::mutex> g(q_m_);
         if (from_retry) {
@@ -351,6 +352,17 @@ void Engine::ingress_loop() {
       q_cv_.notify_all();
       break;
     }
+    case MsgType::RNDZVS_CANCEL: {
+      // the receive that announced this buffer gave up: a later send with the same tag must not write into it
+      std::lock_guard<std::mutex> g(q_m_);
+      for (auto it = addr_notes_.begin(); it != addr_notes_.end(); ++it)
+        if (it->comm_sig == p.hdr.comm_sig && it->src == p.hdr.src && it->tag == p.hdr.tag && it->kind == p.hdr.seqn &&
+            it->vaddr == p.hdr.vaddr) {
+          addr_notes_.erase(it);
+          break;
+        }
+      break;
+    }
     }
   }
 }
@@ -481,7 +493,9 @@ void Engine::progress_parked_sends() {
       const uint64_t dur = now_ns() - c.t0_ns;
       if (c.req) c.req->complete(rc, dur);
       if (c.on_done) c.on_done(rc);
-      // the list closed up: idx already points at the next candidate
+      // the list closed up: idx already points at the next candidate; an elder of the interrupted call is gone,
+      // so that call's own position (and re-insert point) moves down by one
+      if (idx < older_parked_) --older_parked_;
     }
   }
 }

@@ -250,6 +250,36 @@ void Engine::rndzv_post_addr(Ctx &x, uint32_t to_rank, uint64_t vaddr, uint32_t 
   fabric_->send(std::move(p));
 }
 
+// A parked call is being retired with a timeout: remove the mailbox entries that belong to it, here and (for a
+// rendezvous receive, whose address note sits in the sender's mailbox) at the peer.
+void Engine::purge_notes_of(EmuCall &c) {
+  Ctx x;
+  uint32_t e = 0;
+  if (!decode(c, x, e)) return;
+  const bool p2p = x.op == operation::send || x.op == operation::recv;
+  {
+    std::lock_guard<std::mutex> g(q_m_);
+    const uint32_t peer = p2p && x.root < x.comm.size ? x.comm.session[x.root] : 0;
+    addr_notes_.remove_if([&](const AddrNote &n) {
+      return n.comm_sig == x.comm.sig && n.kind == note_kind(x) && (!p2p || (n.src == peer && tag_match(x.tag, n.tag)));
+    });
+    done_notes_.remove_if([&](const DoneNote &n) {
+      return n.comm_sig == x.comm.sig && n.kind == note_kind(x) && (!p2p || (n.src == peer && tag_match(x.tag, n.tag)));
+    });
+  }
+  if (x.op == operation::recv && !x.eager && c.step != 0 && x.root < x.comm.size) {
+    Packet p;
+    p.hdr.msg_type = static_cast<uint32_t>(MsgType::RNDZVS_CANCEL);
+    p.hdr.src = static_cast<uint32_t>(rank_);
+    p.hdr.dst = x.comm.session[x.root];
+    p.hdr.tag = x.tag;
+    p.hdr.vaddr = x.a2;
+    p.hdr.comm_sig = x.comm.sig;
+    p.hdr.seqn = note_kind(x);
+    fabric_->send(std::move(p));
+  }
+}
+
 bool Engine::rndzv_take_addr(Ctx &x, uint32_t from_rank, uint32_t tag, uint64_t &vaddr) {
   std::lock_guard<std::mutex> g(q_m_);
   const uint32_t src = x.comm.session[from_rank];

@@ -1,5 +1,6 @@
 """Worker of tests/test_emulator_multiprocess.py::test_torch_distributed_backend (one process per rank)."""
-import os, sys
+import faulthandler, os, sys
+faulthandler.dump_traceback_later(int(os.environ.get("PG_WATCHDOG_S", 90)), exit=True)  # a hang prints where, then exits
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, torch.distributed as dist
 import accl_b200.parallel.process_group  # noqa
@@ -7,8 +8,9 @@ import accl_b200 as A  # noqa: E402
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 use_cuda = torch.cuda.is_available() and A._C.with_cuda and A._C.cuda_driver_available()
 if use_cuda:  # same choice init_from_env makes inside the backend; then every tensor lives on this rank's GPU
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
-    torch.set_default_device(torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+    os.environ["LOCAL_RANK"] = str(int(os.environ.get("LOCAL_RANK", rank)) % torch.cuda.device_count())  # ranks may share a GPU
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    torch.set_default_device(torch.device("cuda", int(os.environ["LOCAL_RANK"])))
 port = os.environ.get("PG_PORT") or str(int(os.environ.get("MASTER_PORT", 29500)) + 7)
 dist.init_process_group("accl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
 t = torch.full((1000,), float(rank + 1))
@@ -28,6 +30,15 @@ if rank == 0: assert torch.all(r == sum(range(world)))
 if rank == 0: dist.send(torch.arange(10, dtype=torch.float32), dst=1)
 if rank == 1:
     x = torch.empty(10); dist.recv(x, src=0); assert torch.equal(x, torch.arange(10, dtype=torch.float32))
+dist.barrier()
+# sub-groups are communicators on the same engine (each with its own protocol-state bank)
+members = [0, world - 1] if world > 2 else [0, 1]
+sub = dist.new_group(members)
+if rank in members:
+    sgt = torch.full((257,), float(rank + 1)); dist.all_reduce(sgt, group=sub)
+    assert torch.all(sgt == sum(m + 1 for m in members)), sgt[:4]
+    nc = torch.arange(12, dtype=torch.float32).view(3, 4).t()   # non-contiguous destination
+    dist.broadcast(nc, src=members[0], group=sub)
 dist.barrier()
 # DistributedDataParallel on top
 torch.manual_seed(0)

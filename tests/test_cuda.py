@@ -54,8 +54,7 @@ def run(world, fn, cfg=EAGER, **kw):
 
 
 def run_shared_gpu(world, fn, cfg=EAGER, **kw):
-    """All ranks on cuda:0 (a supported deployment: ranks sharing a GPU talk through the same heap windows).
-    Used by the cases whose cross-GPU placement has not been validated on a multi-GPU box yet."""
+    """All ranks on cuda:0 (a supported deployment: ranks sharing a GPU talk through the same heap windows)."""
     return A.run_cuda_ranks([0] * world, fn, cfg, heap_mb=64, max_ctas=4, **kw)
 
 
@@ -327,7 +326,7 @@ def test_stream_operands_and_stream_put():
         if r == 0:
             a.copy_from_stream(d, n)
             assert close(d.host, ref_reduce(w, n, SUM), 1e-5, 1e-5)
-    run_shared_gpu(2, fn, EAGER)
+    run(2, fn, EAGER)
 
 
 def test_large_reduce_is_distributed_over_workers():
@@ -345,16 +344,18 @@ def test_large_reduce_is_distributed_over_workers():
 
 @pytest.mark.parametrize("func", [SUM, MAX])
 def test_large_reduce_12mib_chunked(func):
-    """12 MiB + tail: the size class of the chunked rooted-reduce schemes (docs/roadmap.md #1; with the
-    ACCL_EXPERIMENTAL_REDUCE_PUSH build this is the write-only path, otherwise the distributed pull)."""
+    """12 MiB + tail: the size class of the chunked rooted-reduce schemes — the distributed pull (default) and the
+    write-only push through the scratch area (tuning knob reduce_push)."""
     n = (3 << 20) + 5
 
     def fn(a, r, w):
-        s, d = a.create_buffer(n), a.create_buffer(n)
-        s.host[:] = data(n, r, salt=3)
-        a.reduce(s, d, n, 1, func)
-        if r == 1:
-            assert close(d.host, ref_reduce(w, n, func, salt=3), 1e-5, 1e-4)
+        for push in (0, 1):
+            a.set_tuning("reduce_push", push)
+            s, d = a.create_buffer(n), a.create_buffer(n)
+            s.host[:] = data(n, r, salt=3 + push)
+            a.reduce(s, d, n, 1, func)
+            if r == 1:
+                assert close(d.host, ref_reduce(w, n, func, salt=3 + push), 1e-5, 1e-4), push
     A.run_cuda_ranks(devices(3), fn, RNDZV, heap_mb=256, max_ctas=8)
 
 
@@ -381,17 +382,20 @@ def test_large_bcast_and_reduce_through_the_switch(dtype):
     A.run_cuda_ranks(list(range(w_)), fn, RNDZV, heap_mb=512, max_ctas=16)
 
 
-def test_large_bcast_is_pipelined_over_workers():
+@pytest.mark.parametrize("flags", [0, 1])
+def test_large_bcast_is_pipelined_over_workers(flags):
     n = (33 << 20) + 4   # 132 MiB fp32 (>= 128 MiB): the root deals slices, the workers forward them
+    # flags = 0: one meeting per chunk; flags = 1: one-way "chunk landed" counters (tuning knob bcast_flags)
 
     def fn(a, r, w):
+        a.set_tuning("bcast_flags", flags)
         for root in (0, 1):
             b = a.create_buffer(n)
             if r == root:
                 b.host[:] = data(n, root, salt=root)
             a.bcast(b, n, root)
             assert torch.equal(b.host, data(n, root, salt=root))
-    A.run_cuda_ranks(devices(3), fn, RNDZV, heap_mb=512, max_ctas=8)
+    A.run_cuda_ranks(devices(3), fn, RNDZV, heap_mb=768, max_ctas=8)
 
 
 @pytest.mark.parametrize("cfg", PROTOCOLS)
@@ -414,4 +418,78 @@ def test_stress_sendrecv_ring(cfg):
             if i % 250 == 0 or i == iters - 1:
                 torch.cuda.synchronize()
                 assert float(d.dev[0]) == float(prv * 10000 + i) and float(d.dev[-1]) == float(prv * 10000 + i)
-    run_shared_gpu(2, fn, cfg)
+    run(2, fn, cfg)
+
+
+@pytest.mark.parametrize("count", [(128 << 10) // 4, (256 << 10) // 4 + 3, (1 << 20) // 4])
+def test_allreduce_in_place_rendezvous_oneshot_sizes(count):
+    """In-place all-reduce in the size class of the rendezvous one-shot (everybody pulls everything): a peer must
+    never read a source that its owner has already overwritten with the result — the kernel takes the two-shot
+    body when any rank runs in place."""
+    def fn(a, r, w):
+        b = a.create_buffer(count)
+        for it in range(4):
+            b.dev.copy_(data(count, r, salt=it).cuda(a.cuda_device))
+            a.allreduce(b, b, count, SUM, from_fpga=True, to_fpga=True)
+            torch.cuda.current_stream().synchronize()
+            assert close(b.dev, ref_reduce(w, count, SUM, salt=it), 1e-5, 1e-4), it
+    A.run_cuda_ranks(devices(3), fn, RNDZV, heap_mb=64, max_ctas=8)
+
+
+@pytest.mark.parametrize("cfg", PROTOCOLS)
+@pytest.mark.parametrize("k", [1, 2])
+@pytest.mark.parametrize("delta", [-1, 0, 1])
+def test_sendrecv_segmentation(cfg, k, delta):
+    """count = k * segment + {-1, 0, 1} (reference ACCLSegmentationTest, test/host/xrt/src/test.cpp:345-393, 1154-1159):
+    the eager path cuts messages at the RX-buffer size, rendezvous moves them whole."""
+    seg = (16 << 10) // 4 if cfg is EAGER else 1024 // 4   # elements per eager segment of the configuration
+    count = k * seg + delta
+
+    def fn(a, r, w):
+        s, d = a.create_buffer(count), a.create_buffer(count)
+        s.host[:] = data(count, r)
+        nxt, prv = (r + 1) % w, (r - 1) % w
+        if r % 2 == 0:
+            a.send(s, count, nxt, tag=3)
+            a.recv(d, count, prv, tag=3)
+        else:
+            a.recv(d, count, prv, tag=3)
+            a.send(s, count, nxt, tag=3)
+        assert torch.equal(d.host, data(count, prv))
+        # and through a collective of the same size
+        out = a.create_buffer(count)
+        a.allreduce(s, out, count, SUM)
+        assert close(out.host, ref_reduce(w, count, SUM), 1e-5, 1e-5)
+    run(2, fn, cfg)
+
+
+def test_stream_ids_do_not_interleave():
+    """With the loop-back off, stream id s is served by its own FIFO (reference: ids 9..246 travel as TDEST,
+    dma_mover.cpp:312,644): two stream_puts with different ids can be drained in either order, and the vadd_put
+    user kernel (data.push while computing, then the consumer's data.pull) lands in the id it names."""
+    from accl_b200.ops import stream_pull, vadd_put
+    n = 5000
+
+    def fn(a, r, w):
+        a.set_tuning("stream_loopback", 0)
+        nxt, prv = (r + 1) % w, (r - 1) % w
+        s1, s2, d1, d2 = (a.create_buffer(n) for _ in range(4))
+        s1.host[:] = data(n, r, salt=1)
+        s2.host[:] = data(n, r, salt=2)
+        a.stream_put(s1, n, nxt, 9)
+        a.stream_put(s2, n, nxt, 10)
+        a.barrier()
+        st2 = stream_pull(a, d2, n, stream_id=10)   # the later put first
+        st1 = stream_pull(a, d1, n, stream_id=9)
+        torch.cuda.current_stream().synchronize()
+        assert int(st1.item()) == 0 and int(st2.item()) == 0
+        assert torch.equal(d1.dev.cpu(), data(n, prv, salt=1)) and torch.equal(d2.dev.cpu(), data(n, prv, salt=2))
+        # the reference's vadd_put example: x + 1 pushed into stream 11 of the next rank while computing
+        s1.sync_to_device()
+        st = vadd_put(a, s1, n, nxt, stream_id=11)
+        sp = stream_pull(a, d1, n, stream_id=11)
+        torch.cuda.current_stream().synchronize()
+        assert int(st.item()) == 0 and int(sp.item()) == 0
+        assert torch.equal(d1.dev.cpu(), data(n, prv, salt=1) + 1.0)
+        a.barrier()
+    run(2, fn, EAGER)

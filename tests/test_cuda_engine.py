@@ -249,3 +249,23 @@ def test_device_issued_calls_next_to_host_calls():
         assert close(out.dev, ref_reduce(w, n, SUM) + w)
         assert float(s.host[0]) == sum(range(w))
     run(2, fn, RNDZV)
+
+
+@pytest.mark.parametrize("mode", ["direct", "engine"])
+def test_torch_distributed_backend_on_gpus(mode):
+    """`dist.init_process_group("accl")` with CUDA tensors, one process per rank (torchrun): the collectives,
+    point to point, sub-groups and a DistributedDataParallel step (tests/helpers/pg_worker.py)."""
+    import os
+    import random
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world = 2
+    env = dict(os.environ, PG_PORT=str(random.randint(20000, 30000)), CUDA_DEVICE_MAX_CONNECTIONS="32",
+               ACCL_PG_ENGINE="1" if mode == "engine" else "0")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+                        "127.0.0.1", "--master-port", str(random.randint(30001, 40000)),
+                        os.path.join(root, "tests", "helpers", "pg_worker.py")], cwd=root, env=env, capture_output=True, text=True,
+                       timeout=200)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count(": ok") == world

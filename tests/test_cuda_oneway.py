@@ -237,7 +237,8 @@ def test_cuda_graph_replay_of_small_allreduces():
             a.allreduce(s, d, n, SUM, from_fpga=True, to_fpga=True, run_async=True).free()  # warm-up outside the graph
             st.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=st):
+            # (ranks are threads of one process here: only this thread's calls belong to the capture)
+            with torch.cuda.graph(g, stream=st, capture_error_mode="thread_local"):
                 for _ in range(10):
                     a.allreduce(s, d, n, SUM, from_fpga=True, to_fpga=True, run_async=True).free()
             for _ in range(3):

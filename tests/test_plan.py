@@ -34,12 +34,14 @@ def test_one_way_protocol_selection():
     assert p["algo"] == "ll" and not p["oneshot"]                     # shards of 8 KiB through the flag-in-data protocol
     p = plan(Op.allreduce, 2 << 20, max_eager_bytes=4 << 20, ll_kb=2048)
     assert p["algo"] == "ll" and not p["oneshot"] and p["n_ctas"] == 32   # shards of 256 KiB: 32 K lines over all channels
-    # what does not fit the LL region goes to the slot ring, or to the payload + flag protocol when that is enabled
-    assert plan(Op.allreduce, 2 << 20, max_eager_bytes=4 << 20)["algo"] == "eager"
+    # what does not fit the LL region: the payload + flag protocol when that is enabled, else the slot ring while
+    # that is a handful of segments, else the rendezvous algorithms
+    assert plan(Op.allreduce, 2 << 20, max_eager_bytes=4 << 20)["algo"] == "nvls"
     assert plan(Op.allreduce, 2 << 20, max_eager_bytes=4 << 20, staged_max_bytes=1 << 20)["algo"] == "staged"
-    # sizes that do not split into 16-byte shards go one-shot while small, to the slot ring otherwise
+    assert plan(Op.allgather, 256 << 10, max_eager_bytes=4 << 20)["algo"] == "eager"   # 4 segments of 64 KiB
+    # sizes that do not split into 16-byte shards go one-shot while small, to the other paths otherwise
     assert plan(Op.allreduce, 20000)["oneshot"]
-    assert plan(Op.allreduce, (1 << 20) + 4, max_eager_bytes=4 << 20)["algo"] == "eager"
+    assert plan(Op.allreduce, (1 << 20) + 4, max_eager_bytes=4 << 20)["algo"] == "nvls"
     # per-peer message decides for the others
     assert plan(Op.allgather, 8 << 10)["algo"] == "ll"
     assert plan(Op.reduce_scatter, 16 << 10)["algo"] == "ll"
