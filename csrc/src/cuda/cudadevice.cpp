@@ -59,6 +59,13 @@ public:
       : dev_(d), bytes_(bytes), kind_(kind), wrapped_(wrap) {
     if (kind != bufferKind::host_only) off_ = d->allocator().alloc(std::max<size_t>(bytes, 16), 256);
     else ensure_host();
+    if (wrapped_ && bytes_ >= (64u << 10)) {
+      // caller-owned host memory: page-lock it in place so H2D / D2H run at PCIe speed straight from / into the user's
+      // array (no bounce through a pinned pool); best effort — pageable copies still work if the range cannot be locked
+      cudaSetDevice(dev_->device());
+      registered_ = cudaHostRegister(wrapped_, bytes_, cudaHostRegisterPortable) == cudaSuccess;
+      if (!registered_) cudaGetLastError();
+    }
   }
   ~CudaStorage() override {
     cudaSetDevice(dev_->device());
@@ -71,6 +78,7 @@ public:
       }
     }
     if (pinned_) PinnedPool::get().release(pinned_, pinned_cap_);
+    if (registered_) cudaHostUnregister(wrapped_);
   }
   void *host_ptr() override {
     if (wrapped_) return wrapped_;
@@ -112,6 +120,7 @@ private:
   void *pinned_ = nullptr;
   size_t pinned_cap_ = 0;
   void *wrapped_ = nullptr;
+  bool registered_ = false;
 };
 } // namespace
 

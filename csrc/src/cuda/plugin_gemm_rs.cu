@@ -232,6 +232,20 @@ template <bool PAIR> struct Cfg {
 };
 } // namespace g
 
+// Tile order: groups of GROUP_M tile rows are swept column by column, so the ~(SMs / CTAs per tile) tiles in flight
+// form a near-square GROUP_M x ~9 patch whose A rows and W rows (K-long, 4 MB each at K = 8192) stay in the 126 MB L2.
+// A plain row-major sweep keeps all of W in flight at once: measured 2.2 GB of DRAM reads for an 8192^3 GEMM whose
+// operands are 256 MB (ncu, profiles/ncu_gemm_rs_pair.md) and a tensor pipe waiting on L2 misses.
+template <int GROUP_M>
+__device__ __forceinline__ void tile_coords(uint32_t t, uint32_t tiles_m, uint32_t tiles_n, uint32_t &mo, uint32_t &nb) {
+  const uint32_t width = GROUP_M * tiles_n;
+  const uint32_t group = t / width, first_m = group * GROUP_M;
+  const uint32_t gsize = tiles_m - first_m < static_cast<uint32_t>(GROUP_M) ? tiles_m - first_m : static_cast<uint32_t>(GROUP_M);
+  const uint32_t in = t % width;
+  mo = first_m + in % gsize;
+  nb = in / gsize;
+}
+
 // One epilogue chunk: 32 accumulator rows (this warp's TMEM lanes) x COLS columns -> staged in 128B-swizzled
 // shared memory -> handed to the collective (device API: reduce_scatter_emit_tile).
 template <bool F32>
@@ -272,6 +286,7 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   using C = Cfg<PAIR>;
   constexpr int STAGES = C::STAGES;
   constexpr int COLS = F32 ? 32 : 64; // columns per emitted box: one 128-byte swizzle row
+  constexpr int GROUP_M = PAIR ? 8 : 16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t *smem_a = smem;
@@ -386,7 +401,8 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===== TMA producer (pair: both CTAs, each its 128 rows of A and its 128 rows of W)
     uint32_t stage = 0, phase = 0;
     for (uint32_t t = unit; t < num_tiles; t += num_units) {
-      const uint32_t mo = t / tiles_n, nb = t % tiles_n;
+      uint32_t mo, nb;
+      tile_coords<GROUP_M>(t, tiles_m, tiles_n, mo, nb);
       const uint32_t mb = (mo + (me + 1) * tiles_m_per_rank) % tiles_m; // peers' rows first, mine last
       for (uint32_t kb = 0; kb < k_blocks; ++kb) {
         if (lane == 0) {
@@ -465,7 +481,8 @@ k_plugin_gemm_rs(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t *my_epi = smem_epi + ew * 2 * EPI_BUF_BYTES;
     uint32_t acc = 0, acc_phase = 0, ebuf = 0;
     for (uint32_t t = unit; t < num_tiles; t += num_units) {
-      const uint32_t mo = t / tiles_n, nb = t % tiles_n;
+      uint32_t mo, nb;
+      tile_coords<GROUP_M>(t, tiles_m, tiles_n, mo, nb);
       const uint32_t mb = (mo + (me + 1) * tiles_m_per_rank) % tiles_m;
       const uint32_t row0 = mb * C::TILE_M + cr * BM + ew * 32; // first of this warp's 32 rows
       const uint32_t owner = row0 / rows_per_rank;               // a warp's rows never straddle owners

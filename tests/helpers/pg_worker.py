@@ -12,7 +12,10 @@ if use_cuda:  # same choice init_from_env makes inside the backend; then every t
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     torch.set_default_device(torch.device("cuda", int(os.environ["LOCAL_RANK"])))
 port = os.environ.get("PG_PORT") or str(int(os.environ.get("MASTER_PORT", 29500)) + 7)
-dist.init_process_group("accl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+if "TORCHELASTIC_RUN_ID" in os.environ:   # under torchrun the agent already hosts the store at MASTER_ADDR:MASTER_PORT
+    dist.init_process_group("accl", init_method="env://", rank=rank, world_size=world)
+else:
+    dist.init_process_group("accl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
 t = torch.full((1000,), float(rank + 1))
 dist.all_reduce(t)
 assert torch.all(t == world * (world + 1) / 2), t[:4]
