@@ -24,6 +24,13 @@ SUM = _C.ReduceFunction.SUM
 MAX = _C.ReduceFunction.MAX
 
 
+try:
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # pragma: no cover - older torch
+    def _raw_stream(device):
+        return torch.cuda.current_stream(device).cuda_stream
+
+
 class _CudaView:
     """Minimal __cuda_array_interface__ carrier so torch can alias heap memory."""
 
@@ -114,6 +121,7 @@ class Accl:
         self.world = world
         self.cuda_device = cuda_device
         self.initialized = False
+        self._cuda = impl.device_type() == _C.DeviceType.cuda
 
     # ---- setup -----------------------------------------------------------
     @staticmethod
@@ -174,8 +182,9 @@ class Accl:
 
     # ---- call helpers ----------------------------------------------------
     def _stream(self):
-        if self.is_cuda and self.cuda_device is not None:
-            h = torch.cuda.current_stream(self.cuda_device).cuda_stream
+        if self._cuda and self.cuda_device is not None:
+            # raw handle of torch's current stream (no Stream object: this runs on every call)
+            h = _raw_stream(self.cuda_device)
             # 0 is torch's legacy default stream: name it explicitly (cudaStreamLegacy)
             # so calls stay ordered with tensor ops issued on it
             self._a.set_stream(h if h else 1)

@@ -71,7 +71,7 @@ def _compile(src, with_cuda, hdr_mtime, verbose, force):
     if not force and obj.exists() and obj.stat().st_mtime > max(srcp.stat().st_mtime, hdr_mtime):
         return obj
     defs = ["-DACCL_WITH_CUDA"] if with_cuda else []
-    # opt-in code paths kept out of the default build (see docs/roadmap.md), e.g.
+    # extra -D switches for experiments, e.g.
     # ACCL_EXTRA_DEFINES=ACCL_EXPERIMENTAL_REDUCE_PUSH python -m accl_b200.utils.build -f
     defs += ["-D" + d for d in os.environ.get("ACCL_EXTRA_DEFINES", "").split(",") if d]
     if src.endswith(".cu"):

@@ -29,15 +29,33 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 single CTA per tile, 2 CTA pair (cta_group::2)")
     ap.add_argument("--f32", action="store_true", help="fp32 output shard (fp32 accumulation of the partial products)")
+    ap.add_argument("--shapes", default="", help='several runs in one process: "MxNxK[:f32][:v1|:v2],..." (K per rank)')
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    M, N, K = a.m, a.n, a.k
-    acc = A.cuda_rank(rank, world, local, heap_mb=max(512, (M // world * N * 2 >> 20) * 2 + 256), max_ctas=32)
+    runs = []
+    if a.shapes:
+        for spec in a.shapes.split(","):
+            dims, *opts = spec.split(":")
+            m, n, k = (int(v) for v in dims.lower().split("x"))
+            runs.append((m, n, k, "f32" in opts, 1 if "v1" in opts else 2 if "v2" in opts else a.variant))
+    else:
+        runs.append((a.m, a.n, a.k, a.f32, a.variant))
+    shard_mb = sum((m // world * n * (4 if f32 else 2) >> 20) + 1 for m, n, _, f32, _ in runs)
+    acc = A.cuda_rank(rank, world, local, heap_mb=max(512, shard_mb + 384), max_ctas=32)
     acc.initialize(n_egr_rx_bufs=4, egr_rx_buf_size=16 << 10, max_egr_size=16 << 10, max_rndzv_size=1 << 30)
+    for M, N, K, f32, variant in runs:
+        a.f32, a.variant = f32, variant
+        one(a, acc, rank, world, M, N, K)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def one(a, acc, rank, world, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(7 + rank)
     x = (torch.randn(M, K, device="cuda", generator=g) * 0.25).bfloat16()
     w = (torch.randn(N, K, device="cuda", generator=g) * 0.25).bfloat16()
@@ -122,9 +140,8 @@ def main():
             os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
             with open(a.out, "a") as fh:
                 fh.write(json.dumps(row) + "\n")
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    del x, w, ref_out
+    torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":

@@ -27,16 +27,25 @@ def main():
             continue
         world = int(rows[0]["world"])
         print(f"### {os.path.basename(path)} — {world} x B200, {rows[0]['dtype']}\n")
-        print("| op | size | accl us | accl busbw GB/s | NCCL us | NCCL busbw GB/s | speedup vs NCCL | % of ideal (770 GB/s/dir) |")
-        print("|---|---|---|---|---|---|---|---|")
+        mode = rows[0].get("mode", "direct")
+        print(f"(mode: {mode}; `us` = CUDA-event time per call of a host loop of asynchronous calls, median of batches, max over "
+              f"ranks; `device us` = engine-measured duration of the call itself; `graph us` = per call inside a replayed CUDA graph)\n")
+        print("| op | size | accl us | device us | accl busbw GB/s | NCCL us | NCCL busbw GB/s | speedup vs NCCL | accl graph us | NCCL graph us | "
+              "speedup (graphs) | % of ideal (900 GB/s/dir) |")
+        print("|---|---|---|---|---|---|---|---|---|---|---|---|")
+
+        def f(r, k, fmt="{:.1f}"):
+            v = r.get(k)
+            return fmt.format(float(v)) if v not in (None, "", "None") else "-"
         for r in rows:
             nb = int(r["bytes"])
             a_us = float(r["accl_us"])
             n_us = float(r["nccl_us"]) if r.get("nccl_us") else 0.0
             ideal = ideal_us(r["op"], nb, world)
-            print(f"| {r['op']} | {human(nb)} | {a_us:.1f} | {float(r['accl_busbw']):.1f} | "
+            sg = f(r, "speedup_graph", "{:.2f}x")
+            print(f"| {r['op']} | {human(nb)} | {a_us:.1f} | {f(r, 'accl_device_us')} | {float(r['accl_busbw']):.1f} | "
                   f"{n_us:.1f} | {float(r['nccl_busbw']) if r.get('nccl_busbw') else 0:.1f} | "
-                  f"{(n_us / a_us if n_us else 0):.2f}x | {100 * ideal / a_us:.0f}% |")
+                  f"{(n_us / a_us if n_us else 0):.2f}x | {f(r, 'accl_graph_us')} | {f(r, 'nccl_graph_us')} | {sg} | {100 * ideal / a_us:.0f}% |")
         print()
 
 

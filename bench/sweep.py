@@ -43,6 +43,8 @@ def main():
     ap.add_argument("--graph", action="store_true", help="add CUDA-graph replay columns (ours in direct mode, and NCCL)")
     ap.add_argument("--tune", default="", help="name=value,... runtime knobs, identical on every rank")
     ap.add_argument("--engine-workers", type=int, default=0)
+    ap.add_argument("--compress", default="", help="wire dtype (float16 / bfloat16 / float8_e4m3): all-reduce / all-gather / "
+                    "reduce-scatter run with compress_dtype; the NCCL column stays the uncompressed call")
     ap.add_argument("--oneshot-kb", type=int, default=2048)
     ap.add_argument("--nvls-min-ranks", type=int, default=3)
     ap.add_argument("--engine", action="store_true")
@@ -148,8 +150,10 @@ def main():
             nbytes = 1 << lg
             n = nbytes // esz          # message size in the NCCL-tests sense (total for AG/RS)
             per = n // world           # per-rank block for AG / RS / scatter / gather
-            iters = 200 if nbytes <= (1 << 20) else (50 if nbytes <= (1 << 26) else 15)
+            iters = 100 if nbytes <= (1 << 20) else (40 if nbytes <= (1 << 26) else 15)
             kw = dict(from_fpga=True, to_fpga=True, run_async=True)
+            if args.compress and op in ("allreduce", "allgather", "reduce_scatter"):
+                kw["compress_dtype"] = args.compress if args.compress.startswith("float8") else getattr(torch, args.compress)
             s, d = big_s, big_d
             if op == "allreduce":
                 c = lambda: acc.allreduce(s, d, n, A.SUM, **kw)
@@ -186,7 +190,8 @@ def main():
                 continue
             f = lambda: c().free()  # noqa: E731
             ms = timed(f, iters)
-            row = dict(op=op, bytes=nbytes, dtype=args.dtype, world=world, mode="engine" if args.engine else "direct",
+            row = dict(op=op, bytes=nbytes, dtype=args.dtype, wire=args.compress or args.dtype, world=world,
+                       mode="engine" if args.engine else "direct",
                        accl_us=ms * 1e3, accl_busbw=nbytes / ms * 1e-6 * factor(op, world),
                        accl_device_us=device_us(c) if nbytes <= (64 << 20) else None)
             if args.graph and not args.engine and nbytes <= (4 << 20):

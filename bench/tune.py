@@ -84,9 +84,9 @@ def main():
     whats = args.what.split(",")
     if "allreduce" in whats:
         ref = ref_sum
-        ctas = [32, 64, 96, 128] if args.quick else [32, 48, 64, 80, 96, 128]
-        unroll = [8, 16] if args.quick else [4, 8, 16]
-        hyb = [0, 3] if args.quick else [0, 1, 2, 3, 4, 6]
+        ctas = [16, 24, 32, 48, 64] if args.quick else [16, 24, 32, 48, 64, 80, 96, 128]
+        unroll = [2, 4, 8] if args.quick else [2, 4, 8, 16]
+        hyb = [0] if args.quick else [0, 2, 4]
         f = 2.0 * (world - 1) / world
         for c, u, h in itertools.product(ctas, unroll, hyb):
             for k, v in (("nvls_ctas", c), ("nvls_unroll", u), ("hybrid_16ths", h)):
@@ -100,11 +100,11 @@ def main():
         ms = timed(lambda: dist.all_reduce(x))
         del x
         emit(dict(what="allreduce", mb=args.mb, dtype=args.dtype, world=world, impl="nccl", us=ms * 1e3, busbw=nbytes / ms * 1e-6 * f))
-        for k, v in (("nvls_ctas", 64), ("nvls_unroll", 8), ("hybrid_16ths", 0)):
+        for k, v in (("nvls_ctas", 32), ("nvls_unroll", 4), ("hybrid_16ths", 0)):
             acc.set_tuning(k, v)
     if "reduce" in whats:
         ref = ref_sum
-        for push, c in itertools.product([0, 1], [64, 128]):
+        for push, c in itertools.product([0, 1, 2], [64, 128]):
             acc.set_tuning("reduce_push", push)
             acc.set_tuning("max_ctas", c)
             d.dev.zero_()
@@ -120,7 +120,7 @@ def main():
         acc.set_tuning("max_ctas", 128)
     if "bcast" in whats:
         ref = ref_b
-        for fl, c in itertools.product([0, 1], [64, 128]):
+        for fl, c in itertools.product([0, 1, 2], [64, 128]):
             acc.set_tuning("bcast_flags", fl)
             acc.set_tuning("max_ctas", c)
             if rank != 0:

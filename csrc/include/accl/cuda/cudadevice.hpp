@@ -45,14 +45,14 @@ struct CudaConfig {
   bool engine = false;         // route calls through the persistent engine kernel
   int engine_idle_us = 1000;   // engine kernel parks itself after this idle time (0 = never)
   int engine_workers = 0;      // worker CTAs of the engine (0: max_ctas, never more than SMs - 16)
-  int nvls_ctas = 64;          // channel cap of the NVLS two-shot all-reduce
+  int nvls_ctas = 32;          // channel cap of the NVLS two-shot all-reduce
   size_t stage_bytes = 0;      // staging region per (bank, parity, source) of ALGO_STAGED (0: sized from the heap)
   size_t ll_bytes = 0;         // same for ALGO_LL
-  size_t ll_max_bytes = 1u << 20;    // per-peer message size up to which the flag-in-data protocol is used (if it fits)
+  size_t ll_max_bytes = 2u << 20;    // flag-in-data protocol while message x (P - 1) peers <= this (and it fits the LL area)
   size_t staged_max_bytes = 0;       // per-peer messages that do not fit LL use ALGO_STAGED up to this size (0: never)
   size_t ll_oneshot_max = 32u << 10; // all-reduce: one hop (everybody sends everything) up to this size
   size_t wire_min_bytes = 256u << 10; // compressed-wire collectives from this size on use the fused two-shot
-  Tune tune{0, 8, 0, 0, 0, {0, 0, 0}};
+  Tune tune{0, 4, 0, 0, 0, {0, 0, 0}};
 };
 
 class CudaDevice;

@@ -177,9 +177,9 @@ struct DevWorld {
 // tuning knobs that travel with every call (set from CudaConfig / ACCL_TUNE_* / Accl.set_tuning)
 struct Tune {
   uint8_t hybrid_16ths;  // large NVLS all-reduce: 16ths of every shard handled by the peer two-shot body instead
-  uint8_t nvls_unroll;   // 16-byte multimem accesses in flight per thread: 4, 8 or 16
-  uint8_t reduce_push;   // rooted reduce: 1 = write-only chunked scheme for large messages
-  uint8_t bcast_flags;   // large bcast: 1 = one-way chunk flags instead of a meeting per step
+  uint8_t nvls_unroll;   // 16-byte multimem accesses in flight per thread: 2, 4 (default), 8 or 16
+  uint8_t reduce_push;   // rooted reduce: 1 = write-only chunked scheme for large messages, 2 = the root reduces through the switch at every size
+  uint8_t bcast_flags;   // large bcast: 1 = one-way chunk flags instead of a meeting per step, 2 = never pipelined (single multicast pass)
   uint8_t split_phases;  // NVLS all-reduce: 1 = reduce-scatter and all-gather halves on disjoint CTA sets
   uint8_t pad[3];
 };

@@ -29,7 +29,7 @@ struct PlanCfg {
   uint32_t nvls_ctas;      // channel cap of the NVLS two-shot all-reduce (fewer, fatter CTAs win through the switch)
   uint32_t stg_bytes;      // staging region per (bank, parity, source) of ALGO_STAGED; 0: protocol off
   uint32_t ll_bytes;       // same for ALGO_LL
-  uint32_t ll_max_bytes;   // per-peer message size up to which the flag-in-data protocol is used
+  uint32_t ll_max_bytes;   // flag-in-data protocol while message x (P - 1) peers stays within this many bytes
   uint32_t ll_oneshot_max; // all-reduce: everybody-sends-everything (one hop) up to this size, two hops above
   uint32_t wire_min_bytes; // compressed-wire calls at least this big use the fused two-shot (0: always the slot ring)
   uint32_t staged_max_bytes; // per-peer messages up to this size that do not fit the LL protocol use ALGO_STAGED
@@ -116,7 +116,9 @@ ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
       if ((extra & WF_ONESHOT) && ubytes > 4ull * cfg.ll_oneshot_max && ubytes > (256u << 10)) ok = false;
     }
     if (ok) {
-      uint32_t n = m <= cfg.ll_max_bytes ? plan_staged_ctas(m, true, cfg, cap) : 0;
+      // flag-in-data doubles the wire bytes, and a rank pushes its message to P - 1 peers: the budget is on the fan-out
+      // (measured on 8 x B200: 7 x 128 KiB wins by 1.3x, 7 x 512 KiB loses by 1.3x against the rendezvous paths)
+      uint32_t n = m * (P > 1 ? P - 1 : 1) <= cfg.ll_max_bytes ? plan_staged_ctas(m, true, cfg, cap) : 0;
       if (n) {
         w.algo = ALGO_LL;
       } else {
@@ -129,10 +131,10 @@ ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
         return;
       }
     }
-    // does not fit the staging regions: segment after segment through the slot ring only while that is a handful of
-    // segments, else the rendezvous algorithms (measured: 4 MiB all-gather on 2 GPUs 45 us through the slots, 17 us
-    // between user buffers)
-    if (ubytes > 8ull * exch[exchmem::EAGER_RX_BUF_SIZE / 4]) eager_ok = false;
+    // does not fit (or is too fat for) the staging regions: through the slot ring only while that is one or two
+    // segments (every segment costs a credit + header + flag round), else the rendezvous algorithms (measured: 4 MiB
+    // all-gather on 2 GPUs 45 us through the slots, 17 us between user buffers)
+    if (ubytes > 2ull * exch[exchmem::EAGER_RX_BUF_SIZE / 4]) eager_ok = false;
   }
   // compressed wire, uncompressed operands, large message: the cast is fused into the two-shot exchange
   // (compress.cuh) instead of pushing segment after segment through the slot ring
@@ -161,9 +163,10 @@ ACCL_HD void plan_call(const uint32_t *exch, const PlanCfg &cfg, WorkItem &w) {
   if (op == operation::allreduce && ubytes * P <= cfg.oneshot_max_bytes) w.algo = ALGO_P2P_ONESHOT;
   if (p2p) w.algo = ALGO_P2P;
   uint32_t c = cap;
-  // measured on 8 x B200 (profiles/sweep_8gpu_{nvls,p2p}*.csv, 64 vs 128 CTAs): two-shot all-reduce through the
-  // switch is 5-25 % faster with 64 channels at every size (fewer flag round trips per byte); peer loads / stores
-  // want every channel they can get (2 x B200: 64 MiB in 189 us with 64 CTAs, 120 us with 128)
+  // measured on 8 x B200 (profiles/tune_8gpu_*.jsonl: 32 ... 128 channels x 4 / 8 / 16 accesses in flight): two-shot
+  // all-reduce through the switch is fastest with FEW channels and short bursts (256 MiB fp32: 796 GB/s with 32 x 4,
+  // 772 with 64 x 8, 714 with 128 x 16); peer loads / stores want every channel they can get (2 x B200: 64 MiB in
+  // 189 us with 64 CTAs, 120 us with 128)
   if (op == operation::allreduce && w.algo == ALGO_NVLS && cfg.nvls_ctas && c > cfg.nvls_ctas) c = cfg.nvls_ctas;
   w.n_ctas = plan_ctas(moved, 128u << 10, c);
 }

@@ -68,7 +68,7 @@ void bind_cuda(py::module_ &m) {
     cfg.heap_world = world;
     cfg.oneshot_max_bytes = oneshot_max_bytes;
     cfg.nvls_ops = NVLS_OPS_DEFAULT;
-    cfg.nvls_ctas = 64;
+    cfg.nvls_ctas = 32;
     cfg.stg_bytes = stage_kb << 10;
     cfg.ll_bytes = ll_kb << 10;
     cfg.ll_max_bytes = ll_max_bytes;
@@ -92,7 +92,7 @@ void bind_cuda(py::module_ &m) {
   }, py::arg("op"), py::arg("count"), py::arg("dtype"), py::arg("world"), py::arg("max_eager_bytes") = 65536,
         py::arg("max_ctas") = 128, py::arg("has_mc") = true, py::arg("nvls_min_ranks") = 3,
         py::arg("oneshot_max_bytes") = 2u << 20, py::arg("compressed") = false, py::arg("stage_kb") = 1024, py::arg("ll_kb") = 256,
-        py::arg("ll_max_bytes") = 1 << 20, py::arg("ll_oneshot_max") = 32768, py::arg("staged_max_bytes") = 0,
+        py::arg("ll_max_bytes") = 2 << 20, py::arg("ll_oneshot_max") = 32768, py::arg("staged_max_bytes") = 0,
         py::arg("engine_mode") = false);
   m.def("cuda_set_tuning", [](ACCL &a, const std::string &name, long value) {
     auto *d = dynamic_cast<CudaDevice *>(a.device());

@@ -585,7 +585,8 @@ __device__ __noinline__ void rvb_move(const Ctx &c, EgrPattern pat, const uint64
   const char *src = c.heap(c.w.rank) + it.desc.addr0();
   const bool mc_ok = (it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && all_equal(s_off2, P) && (blk & 15) == 0 &&
                      (s_off2[0] & 15) == 0 && (it.desc.addr0() & 15) == 0;
-  bool bcast_pipelined = stepwise_ok && pat == EP_BCAST && P >= 3 && blk >= (128u << 20) && (blk & 15) == 0;
+  // tune.bcast_flags == 2: never pipeline, the root stores through the switch (or to every peer) in one pass
+  bool bcast_pipelined = stepwise_ok && pat == EP_BCAST && P >= 3 && blk >= (128u << 20) && (blk & 15) == 0 && it.tune.bcast_flags != 2;
   for (uint32_t q = 0; q < P; ++q) bcast_pipelined = bcast_pipelined && (s_off2[q] & 15) == 0;
   switch (pat) {
   case EP_ALLGATHER:
@@ -600,7 +601,7 @@ __device__ __noinline__ void rvb_move(const Ctx &c, EgrPattern pat, const uint64
     break;
   case EP_BCAST:
     if (bcast_pipelined) {
-      if (it.tune.bcast_flags) rv_bcast_flags(c, s_off2);
+      if (it.tune.bcast_flags == 1) rv_bcast_flags(c, s_off2);
       else rv_bcast_pipelined(c, s_off2);
     } else if (me == root) {
       if (mc_ok) {
@@ -724,10 +725,11 @@ __device__ __noinline__ void rvb_reduce(const Ctx &c, const uint64_t *s_off0, co
   const bool use_mc = (it.flags & WF_USE_MC) && it.algo == ALGO_NVLS && nop != NvOp::none && sym;
   char *root_dst = c.heap(c.g(root)) + s_off2[root];
   const size_t nvec = count * es / 16;
-  const bool distributed = P >= 3 && count * es >= (1u << 20) && (s_off2[root] & 15) == 0;
+  // tune.reduce_push == 2: the root lets the switch reduce the whole message (one hop, root inbound = N) at every size
+  const bool distributed = P >= 3 && count * es >= (1u << 20) && (s_off2[root] & 15) == 0 && !(it.tune.reduce_push == 2 && use_mc);
   size_t done = 0;
   // all ranks take the same decision: it only depends on the call and on the (identical) geometry
-  if (stepwise_ok && it.tune.reduce_push && distributed && count * es >= (8u << 20) && all_aligned16(s_off0, P))
+  if (stepwise_ok && it.tune.reduce_push == 1 && distributed && count * es >= (8u << 20) && all_aligned16(s_off0, P))
     done = rv_reduce_push(c, s_off0, s_off2) * 16 / es;
   if (done) {
     // handled above; the sub-vector tail (if any) is reduced by the root below

@@ -457,9 +457,9 @@ PlanCfg CudaDevice::plan_cfg() const {
 bool CudaDevice::set_tuning(const std::string &name, long v) {
   std::lock_guard<std::mutex> lk(m_);
   if (name == "hybrid_16ths") cfg_.tune.hybrid_16ths = static_cast<uint8_t>(std::max(0l, std::min(15l, v)));
-  else if (name == "nvls_unroll") cfg_.tune.nvls_unroll = static_cast<uint8_t>(v == 4 || v == 16 ? v : 8);
-  else if (name == "reduce_push") cfg_.tune.reduce_push = v ? 1 : 0;
-  else if (name == "bcast_flags") cfg_.tune.bcast_flags = v ? 1 : 0;
+  else if (name == "nvls_unroll") cfg_.tune.nvls_unroll = static_cast<uint8_t>(v == 2 || v == 8 || v == 16 ? v : 4);
+  else if (name == "reduce_push") cfg_.tune.reduce_push = static_cast<uint8_t>(v < 0 || v > 2 ? 0 : v);
+  else if (name == "bcast_flags") cfg_.tune.bcast_flags = static_cast<uint8_t>(v < 0 || v > 2 ? 0 : v);
   else if (name == "split_phases") cfg_.tune.split_phases = v ? 1 : 0;
   else if (name == "nvls_ctas") cfg_.nvls_ctas = static_cast<int>(v);
   else if (name == "nvls_min_ranks") cfg_.nvls_min_ranks = static_cast<int>(v);

@@ -474,7 +474,7 @@ __device__ void engine_control(const DevWorld &w, HostRing *hr, int nworkers) {
   __shared__ uint32_t s_order[MAX_ACTIVE]; // active slots, oldest first
   __shared__ uint32_t s_nactive;
   __shared__ uint32_t s_flag, s_err, s_leave;
-  __shared__ unsigned long long s_moves;
+  __shared__ unsigned long long s_moves, s_host_fetched;
   Ctrl *me = my_ctrl(w);
   EngineArea *ea = engine_area(w);
   const uint32_t t = threadIdx.x;
@@ -484,19 +484,19 @@ __device__ void engine_control(const DevWorld &w, HostRing *hr, int nworkers) {
   if (t == 0) {
     s_nactive = 0;
     s_moves = dev::ld_acquire_gpu(&me->move_tail);
+    s_host_fetched = me->host_fetched;
     s_leave = 0;
     hr->state = ENG_RUNNING;
   }
   __syncthreads();
   EngCtx e{w, me, ea, nworkers, &s_moves, &s_flag};
   unsigned long long fetched = me->cmd_fetched;
-  unsigned long long host_fetched = me->host_fetched;
   unsigned long long last_work_ns = dev::globaltimer_ns();
   const uint32_t idle_us = hr->idle_us;
   for (;;) {
     bool progressed = false;
-    // ---- fetch new commands while there is room
-    for (;;) {
+    // ---- fetch new commands while there is room (at most a few per pass: a fresh command is stepped right away)
+    for (int nf = 0; nf < 4; ++nf) {
       uint32_t have = 0;
       if (t == 0 && s_nactive < static_cast<uint32_t>(MAX_ACTIVE))
         have = dev::ld_acquire_sys(&me->cmd_ready[fetched % RING_SLOTS]) == fetched + 1 ? 1u : 0u;
@@ -526,7 +526,7 @@ __device__ void engine_control(const DevWorld &w, HostRing *hr, int nworkers) {
           }
           cl.item = wi;
         } else {
-          host_fetched += 1;
+          s_host_fetched += 1;
         }
         cl.item.flags |= WF_ENGINE;
         cl.ticket1 = fetched + 1;
@@ -538,14 +538,14 @@ __device__ void engine_control(const DevWorld &w, HostRing *hr, int nworkers) {
         cl.active = 1;
         s_order[s_nactive] = slot;
         s_nactive += 1;
+        // producers wait on cmd_fetched only when the ring is full: plain stores, ordered by the fences of later steps
         me->cmd_fetched = fetched + 1;
-        me->host_fetched = host_fetched;
-        __threadfence();
+        me->host_fetched = s_host_fetched;
       }
       __syncthreads();
-      host_fetched = me->host_fetched;
       ++fetched;
       progressed = true;
+      if (s_nactive == 1) break; // nothing else in flight: run it now
     }
     // ---- step every call in flight, oldest first
     for (uint32_t i = 0; i < s_nactive; ++i) {
@@ -601,7 +601,7 @@ __device__ void engine_control(const DevWorld &w, HostRing *hr, int nworkers) {
         if (stop || (idle_long && s_nactive == 0 && hr->pins == 0)) {
           hr->state = ENG_EXITING;
           dev::fence_sc_sys();
-          const bool pending = hr->submitted != host_fetched || dev::ld_acquire_sys(&me->cmd_ready[fetched % RING_SLOTS]) == fetched + 1;
+          const bool pending = hr->submitted != s_host_fetched || dev::ld_acquire_sys(&me->cmd_ready[fetched % RING_SLOTS]) == fetched + 1;
           if ((pending || s_nactive != 0) && !stop) hr->state = ENG_RUNNING; // a submit raced with parking: keep going
           else leave = 1;
         }

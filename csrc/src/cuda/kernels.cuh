@@ -483,6 +483,7 @@ template <NvOp OP, bool MC_OUT>
 __device__ __forceinline__ void nvls_reduce_unroll(uint32_t unroll, const char *mc_in, char *out, size_t v0, size_t v1, int cta,
                                                    int nctas) {
   if (unroll == 4) nvls_reduce_range<OP, MC_OUT, 4>(mc_in, out, v0, v1, cta, nctas);
+  else if (unroll == 2) nvls_reduce_range<OP, MC_OUT, 2>(mc_in, out, v0, v1, cta, nctas);
   else if (unroll == 16) nvls_reduce_range<OP, MC_OUT, 16>(mc_in, out, v0, v1, cta, nctas);
   else nvls_reduce_range<OP, MC_OUT, 8>(mc_in, out, v0, v1, cta, nctas);
 }

@@ -38,7 +38,8 @@ def test_one_way_protocol_selection():
     # that is a handful of segments, else the rendezvous algorithms
     assert plan(Op.allreduce, 2 << 20, max_eager_bytes=4 << 20)["algo"] == "nvls"
     assert plan(Op.allreduce, 2 << 20, max_eager_bytes=4 << 20, staged_max_bytes=1 << 20)["algo"] == "staged"
-    assert plan(Op.allgather, 256 << 10, max_eager_bytes=4 << 20)["algo"] == "eager"   # 4 segments of 64 KiB
+    assert plan(Op.allgather, 128 << 10, max_eager_bytes=4 << 20, ll_kb=128)["algo"] == "eager"   # 2 segments of 64 KiB
+    assert plan(Op.allgather, 256 << 10, max_eager_bytes=4 << 20)["algo"] == "p2p"     # 4 segments: user buffer to user buffer
     # sizes that do not split into 16-byte shards go one-shot while small, to the other paths otherwise
     assert plan(Op.allreduce, 20000)["oneshot"]
     assert plan(Op.allreduce, (1 << 20) + 4, max_eager_bytes=4 << 20)["algo"] == "nvls"
@@ -49,6 +50,14 @@ def test_one_way_protocol_selection():
     assert plan(Op.bcast, 32 << 10, ll_max_bytes=16384, staged_max_bytes=1 << 20)["algo"] == "staged"   # the crossover is a knob
     assert plan(Op.allgather, 256 << 10, max_eager_bytes=1 << 20, staged_max_bytes=1 << 20)["algo"] == "staged"   # 256 KiB > LL capacity of 128 KiB
     assert plan(Op.allgather, 256 << 10, max_eager_bytes=1 << 20, ll_kb=2048)["algo"] == "ll"
+    # flag-in-data doubles the wire bytes: budgeted on message x (P - 1) peers (2 MiB), so the crossover moves with P
+    big = dict(max_eager_bytes=4 << 20, ll_kb=2048)
+    assert plan(Op.allgather, 256 << 10, world=8, **big)["algo"] == "ll"      # 7 x 256 KiB
+    assert plan(Op.allgather, 512 << 10, world=8, **big)["algo"] == "p2p"     # 7 x 512 KiB: user buffer to user buffer
+    assert plan(Op.allgather, 512 << 10, world=4, **big)["algo"] == "ll"      # 3 x 512 KiB
+    assert plan(Op.allreduce, 4 << 20, world=8, **big)["algo"] == "nvls"      # shards of 512 KiB to 7 peers
+    assert plan(Op.allreduce, 2 << 20, world=2, **big)["algo"] == "ll"        # one shard of 1 MiB to one peer
+    assert plan(Op.bcast, 512 << 10, world=8, **big)["algo"] == "nvls"        # the root would push 7 x 512 KiB x 2
     # no staging configured: everything one-way is the slot ring
     assert plan(Op.allreduce, 1024, stage_kb=0, ll_kb=0)["algo"] == "eager"
     # channel counts: every channel owns 1/32 of a region
@@ -77,7 +86,7 @@ def test_nvls_only_for_ops_that_win_through_the_switch():
 
 
 def test_channel_counts():
-    assert plan(Op.allreduce, 256 << 20, max_ctas=128)["n_ctas"] == 64      # measured: 64 beats 128 through the switch
+    assert plan(Op.allreduce, 256 << 20, max_ctas=128)["n_ctas"] == 32      # measured: few channels win through the switch
     assert plan(Op.allreduce, 64 << 20, world=2, max_ctas=128)["n_ctas"] == 128    # peer loads / stores want them all
     assert plan(Op.allreduce, 256 << 20, world=2, max_ctas=128)["n_ctas"] == 128
     assert plan(Op.reduce_scatter, 32 << 20, max_ctas=128)["n_ctas"] == 128  # 8 x 32 MiB moved: all channels
