@@ -115,11 +115,27 @@ class TensorGroup:
         buf = getattr(t, "_accl_buffer", None)
         if buf is not None and buf.length == t.numel():
             return buf, False
-        # stage through a cached heap buffer of the right size / dtype
-        key = (role, t.dtype, t.numel())
-        if key not in self._scratch:
+        # stage through ONE cached heap buffer per (role, dtype); it grows to the largest tensor seen (calls carry
+        # their own element counts, so a longer buffer is fine).  Reuse is safe: staging copies and collectives are
+        # ordered on the caller's stream.
+        key = (role, t.dtype)
+        cur = self._scratch.get(key)
+        if cur is None or cur.length < t.numel():
+            self._scratch.pop(key, None)
+            cur = None  # the old allocation returns to the heap (same order on every rank) before the new one is made
             self._scratch[key] = self.accl.create_buffer(t.numel(), t.dtype)
         return self._scratch[key], True
+
+    def _chunks(self, t: torch.Tensor):
+        """Element-wise collectives on a tensor outside the heap that is larger than the staging budget: contiguous
+        views of at most `scratch_bytes` each (None when the tensor can go in one piece)."""
+        if getattr(t, "_accl_buffer", None) is not None or t.numel() * t.element_size() <= self._scratch_bytes:
+            return None
+        step = max(1, self._scratch_bytes // t.element_size())
+        flat = t.view(-1) if t.is_contiguous() else None
+        if flat is None:
+            return None
+        return [flat[o:o + step] for o in range(0, t.numel(), step)]
 
     def _run(self, fn, src: torch.Tensor, dst: torch.Tensor, src_elems, dst_elems):
         sb, s_staged = self._buffer_of(src, "s")
@@ -133,10 +149,20 @@ class TensorGroup:
 
     # -- collectives ---------------------------------------------------------
     def all_reduce(self, t: torch.Tensor, op=SUM):
+        parts = self._chunks(t)
+        if parts:
+            for p in parts:
+                req = self.all_reduce(p, op)
+            return req
         n = t.numel()
         return self._run(lambda s, d: self.accl.allreduce(s, d, n, op, self.comm_id, self._res, self._res, run_async=self._async), t, t, n, n)
 
     def broadcast(self, t: torch.Tensor, root=0):
+        parts = self._chunks(t)
+        if parts:
+            for p in parts:
+                req = self.broadcast(p, root)
+            return req
         n = t.numel()
         return self._run(lambda s, d: self.accl.bcast(s, n, root, self.comm_id, self._res, self._res, run_async=self._async), t, t, n, n)
 

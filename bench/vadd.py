@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--max-ctas", type=int, default=64)
     ap.add_argument("--engine-workers", type=int, default=48)
-    ap.add_argument("--chunk-kb", type=int, default=4096, help="bytes of x + y handed to the engine per device-issued all-reduce")
+    ap.add_argument("--chunk-kb", type=int, default=0, help="bytes of x + y handed to the engine per device-issued all-reduce")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))

@@ -24,6 +24,7 @@ public:
   void stop();
   // device-side clients (plugin kernels) are about to issue commands: keep the engine resident
   void pin();
+  void pin_resident(); // first device-side client: stay resident from now on (no host callback per launch)
   void unpin();
   struct Impl;
 

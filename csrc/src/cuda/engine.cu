@@ -809,6 +809,7 @@ struct Engine::Impl {
   cudaStream_t stream = nullptr;
   unsigned long long submitted = 0;
   int nworkers = 0;
+  bool resident = false;
   std::mutex m;
 };
 
@@ -892,6 +893,16 @@ void Engine::pin() {
   std::lock_guard<std::mutex> g(impl_->m);
   impl_->ring->pins = impl_->ring->pins + 1;
   std::atomic_thread_fence(std::memory_order_seq_cst);
+  ensure_running_locked();
+}
+
+void Engine::pin_resident() {
+  std::lock_guard<std::mutex> g(impl_->m);
+  if (!impl_->resident) {
+    impl_->resident = true;
+    impl_->ring->pins = impl_->ring->pins + 1;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+  }
   ensure_running_locked();
 }
 

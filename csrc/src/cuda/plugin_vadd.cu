@@ -162,19 +162,24 @@ cudaError_t launch_stream_pull(CudaDevice &dev, uint64_t dst_off, uint32_t count
   return cudaGetLastError();
 }
 
-static void CUDART_CB unpin_cb(void *user) { static_cast<Engine *>(user)->unpin(); }
-
 cudaError_t launch_vadd_allreduce(CudaDevice &dev, uint64_t x_off, uint64_t y_off, uint64_t tmp_off, uint64_t out_off,
                                   uint32_t count, uint32_t chunk_elems, uint32_t comm_adr, uint32_t dpcfg_adr, uint32_t *status_dev,
                                   cudaStream_t stream) {
   Engine *eng = dev.engine();
   if (!eng) throw std::runtime_error("vadd_allreduce plugin needs the persistent engine (engine=True)");
   ACCL_CUDART(cudaSetDevice(dev.device()));
-  if (chunk_elems == 0) chunk_elems = 1u << 20; // 4 MiB of fp32 per collective
+  if (chunk_elems == 0) {
+    // every chunk costs one trip through the engine (~10 us more than its transfer time) and only the first chunk's
+    // compute is exposed: few, large chunks
+    const uint64_t bytes = static_cast<uint64_t>(count) * 4;
+    const uint32_t nchunks = bytes <= (8u << 20) ? 1 : bytes <= (64u << 20) ? 2 : 4;
+    chunk_elems = (count + nchunks - 1) / nchunks;
+    chunk_elems = (chunk_elems + 1023) & ~1023u; // shards of every chunk stay 16-byte aligned for up to 64 ranks
+  }
   chunk_elems = (chunk_elems + 3) & ~3u;
   while ((count + chunk_elems - 1) / chunk_elems > VADD_MAX_CHUNKS) chunk_elems *= 2;
   VaddState *st = reinterpret_cast<VaddState *>(dev.plugin_scratch(sizeof(VaddState)));
-  eng->pin(); // keep the engine resident while a device-side client may issue commands
+  eng->pin_resident(); // a device-side client may issue commands at any time from now on: the engine does not park
   // the engine's CTAs stay resident next to this kernel: leave them (and a few spare) their SMs
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev.device());
@@ -183,9 +188,7 @@ cudaError_t launch_vadd_allreduce(CudaDevice &dev, uint64_t x_off, uint64_t y_of
   const uint32_t grid = std::min<uint32_t>(static_cast<uint32_t>(avail), want);
   k_plugin_vadd_allreduce<<<grid, 512, 0, stream>>>(dev.world(), x_off, y_off, tmp_off, out_off, count, chunk_elems, comm_adr,
                                                     dpcfg_adr, st, status_dev);
-  cudaError_t e = cudaGetLastError();
-  cudaLaunchHostFunc(stream, unpin_cb, eng);
-  return e;
+  return cudaGetLastError();
 }
 
 } // namespace cuda

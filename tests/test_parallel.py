@@ -38,6 +38,26 @@ def test_tensor_group_collectives():
     A.run_ranks(W, fn, CFG)
 
 
+def test_staging_is_bounded_large_tensors_go_in_chunks():
+    """Tensors outside the heap are staged through one buffer per (role, dtype); beyond `scratch_bytes`
+    all_reduce / broadcast run chunk by chunk (DDP's 250 MB parameter broadcast must not exhaust the heap)."""
+    def fn(a, r, w):
+        g = TensorGroup(a, scratch_bytes=4096)                       # 1024 floats per chunk
+        t = torch.arange(5000, dtype=torch.float32) * (r + 1)
+        g.all_reduce(t)
+        assert torch.equal(t, torch.arange(5000, dtype=torch.float32) * sum(range(1, w + 1)))
+        b = torch.full((3000,), float(r))
+        g.broadcast(b, root=2)
+        assert torch.all(b == 2.0)
+        for n in (10, 700, 20, 1024):                                # different sizes share (and grow) one staging buffer
+            u = torch.full((n,), 1.0)
+            g.all_reduce(u)
+            assert torch.all(u == w)
+        assert len(g._scratch) == 1 and max(len(v) for v in g._scratch.values()) == 1024
+        g.barrier()
+    A.run_ranks(W, fn, CFG)
+
+
 def test_ring_exchange_and_grad_bucket():
     def fn(a, r, w):
         g = TensorGroup(a)
