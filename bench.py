@@ -254,8 +254,12 @@ def main():
         }
         if world > 1:
             # bytes per direction per GPU: in-switch two-shot moves M (1 + 1/P), peer two-shot 2 M (P-1)/P
-            out["link_GBps_per_dir_nvls_accounting"] = nbytes * (1 + 1.0 / world) / ms * 1e-6
-            out["frac_of_900_GBps_link"] = out["link_GBps_per_dir_nvls_accounting"] / 900.0
+            # (the NVLink byte counters confirm both: profiles/nvlink_traffic_*.jsonl)
+            in_switch = "nvls=yes" in str(result.get("backend", "")) and world >= 3
+            per_dir = nbytes * (1 + 1.0 / world) if in_switch else 2.0 * nbytes * (world - 1) / world
+            out["link_GBps_per_dir"] = per_dir / ms * 1e-6
+            out["link_accounting"] = "in-switch two-shot: M (1 + 1/P)" if in_switch else "peer two-shot: 2 M (P-1)/P"
+            out["frac_of_900_GBps_link"] = out["link_GBps_per_dir"] / 900.0
         if e2e is not None:
             out["e2e"] = e2e
         out.update(result)

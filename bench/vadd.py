@@ -10,6 +10,7 @@ chunk over NVLink — no host on the path after the launch, compute and communic
 CUDA events, max over ranks.  Note: the engine mode needs `CUDA_DEVICE_MAX_CONNECTIONS >= 2`; the launcher sets 32.
 """
 import argparse
+import faulthandler
 import json
 import os
 import sys
@@ -33,6 +34,7 @@ def main():
     ap.add_argument("--chunk-kb", type=int, default=0, help="bytes of x + y handed to the engine per device-issued all-reduce")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", 90)), exit=True)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
