@@ -168,6 +168,41 @@ class Accl:
     def create_buffer_p2p(self, length, dtype=DataType.float32):
         return self.create_buffer(length, dtype, BufferKind.p2p)
 
+    # -- zero-copy operands for torch tensors (CUDA backend) -----------------
+    def heap_contains(self, t) -> bool:
+        """True when the CUDA tensor `t` lives inside this rank's symmetric heap (a `Buffer.dev` view, or a tensor
+        allocated from `heap_mem_pool()`)."""
+        if not (self.is_cuda and isinstance(t, torch.Tensor) and t.is_cuda and t.numel()):
+            return False
+        base, size = _C.cuda_heap_range(self._a)
+        p = t.data_ptr()
+        return base <= p and p + t.numel() * t.element_size() <= base + size
+
+    def wrap_device(self, t: "torch.Tensor") -> "Buffer":
+        """A Buffer over a contiguous CUDA tensor that already lives in the heap: zero-copy operand, nothing is
+        allocated.  The tensor must stay alive while calls on the buffer are in flight."""
+        assert t.is_contiguous(), "wrap_device needs a contiguous tensor"
+        b = Buffer(_C.cuda_wrap_device(self._a, t.data_ptr(), t.numel(), to_accl(t.dtype)), self)
+        b._dev = t.view(-1)
+        return b
+
+    def heap_mem_pool(self):
+        """A `torch.cuda.MemPool` whose allocations come from the symmetric heap:
+
+            pool = accl.heap_mem_pool()
+            with torch.cuda.use_mem_pool(pool):
+                ddp = DistributedDataParallel(model, ...)      # gradient buckets land in the heap
+                x = torch.empty(n, device="cuda")               # so does this
+
+        Tensors allocated this way are zero-copy operands of every collective (`TensorGroup` / the "accl"
+        torch.distributed backend recognise them).  Every rank must allocate in the same order."""
+        if getattr(self, "_mem_pool", None) is None:
+            _C.cuda_heap_pool_attach(self._a)
+            alloc = torch.cuda.memory.CUDAPluggableAllocator(_C.__file__, "accl_heap_pool_alloc", "accl_heap_pool_free")
+            self._pool_allocator = alloc
+            self._mem_pool = torch.cuda.MemPool(alloc.allocator())
+        return self._mem_pool
+
     def wrap(self, array):
         """Wrap caller-owned host memory (numpy array or CPU torch tensor)."""
         if isinstance(array, torch.Tensor):

@@ -41,6 +41,8 @@ def init_from_env(backend=None, **kw):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         if "engine" not in kw and os.environ.get("ACCL_PG_ENGINE") is not None:
             kw["engine"] = os.environ["ACCL_PG_ENGINE"] not in ("", "0")
+        if "heap_mb" not in kw and os.environ.get("ACCL_HEAP_MB"):
+            kw["heap_mb"] = int(os.environ["ACCL_HEAP_MB"])   # symmetric heap per rank (default 1024)
         acc = cuda_rank(**kw)
         init_kw.setdefault("n_egr_rx_bufs", 4)
         init_kw.setdefault("egr_rx_buf_size", 64 << 10)
@@ -61,6 +63,7 @@ class TensorGroup:
         self.world = len(accl.get_comm_group(comm_id))
         self.rank = accl.get_comm_rank(comm_id)
         self._scratch = {}
+        self._wrapped = {}  # heap-resident torch tensors seen so far -> Buffer views
         self._scratch_bytes = scratch_bytes
         # CUDA: operands are device resident and calls are stream ordered.  Emulator: the tensor side of a
         # buffer is its host mirror, so calls are blocking and sync to / from the engine's memory themselves.
@@ -115,6 +118,15 @@ class TensorGroup:
         buf = getattr(t, "_accl_buffer", None)
         if buf is not None and buf.length == t.numel():
             return buf, False
+        if self._res and t.is_contiguous() and self.accl.heap_contains(t):
+            # memory from the heap pool (Accl.heap_mem_pool): zero-copy, the view is cached by address
+            key = (t.data_ptr(), t.numel(), t.dtype)
+            buf = self._wrapped.get(key)
+            if buf is None:
+                if len(self._wrapped) > 256:
+                    self._wrapped.clear()
+                buf = self._wrapped[key] = self.accl.wrap_device(t)
+            return buf, False
         # stage through ONE cached heap buffer per (role, dtype); it grows to the largest tensor seen (calls carry
         # their own element counts, so a longer buffer is fine).  Reuse is safe: staging copies and collectives are
         # ordered on the caller's stream.
@@ -130,6 +142,8 @@ class TensorGroup:
         """Element-wise collectives on a tensor outside the heap that is larger than the staging budget: contiguous
         views of at most `scratch_bytes` each (None when the tensor can go in one piece)."""
         if getattr(t, "_accl_buffer", None) is not None or t.numel() * t.element_size() <= self._scratch_bytes:
+            return None
+        if self._res and self.accl.heap_contains(t):
             return None
         step = max(1, self._scratch_bytes // t.element_size())
         flat = t.view(-1) if t.is_contiguous() else None

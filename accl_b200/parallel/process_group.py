@@ -220,4 +220,13 @@ def _create(opts, pg_options=None):
     return AcclProcessGroup(ranks.index(accl.rank), len(ranks), accl, comm)
 
 
+def heap_mem_pool():
+    """`torch.cuda.MemPool` over the symmetric heap of the default "accl" group (see `Accl.heap_mem_pool`): build the
+    DDP wrapper (or allocate gradient / activation buffers) inside `with torch.cuda.use_mem_pool(pool):` and the
+    backend's collectives take those tensors as zero-copy operands instead of staging them through the heap."""
+    if "accl" not in _primary:
+        raise RuntimeError('init_process_group("accl") first')
+    return _primary["accl"].heap_mem_pool()
+
+
 dist.Backend.register_backend("accl", _create, extended_api=True, devices=["cpu", "cuda"])

@@ -21,6 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--backend", default="accl", choices=["accl", "nccl"])
     ap.add_argument("--engine", action="store_true")
+    ap.add_argument("--heap-buckets", action="store_true", help="accl: allocate DDP's gradient buckets in the symmetric heap (zero-copy all-reduce)")
     ap.add_argument("--layers", type=int, default=8)
     ap.add_argument("--width", type=int, default=4096)
     ap.add_argument("--batch", type=int, default=64)
@@ -32,6 +33,7 @@ def main():
     dev = torch.device("cuda", local)
     if a.backend == "accl":
         os.environ["ACCL_PG_ENGINE"] = "1" if a.engine else "0"
+        os.environ.setdefault("ACCL_HEAP_MB", "4096")
         import accl_b200.parallel.process_group  # noqa: F401  (registers the backend)
     dist.init_process_group(a.backend, init_method="env://", rank=rank, world_size=world, **({"device_id": dev} if a.backend == "nccl" else {}))
     torch.manual_seed(0)
@@ -39,7 +41,13 @@ def main():
     for _ in range(a.layers):
         layers += [torch.nn.Linear(a.width, a.width), torch.nn.GELU()]
     model = torch.nn.Sequential(*layers).to(dev)
-    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local] if a.backend == "nccl" else None, bucket_cap_mb=64)
+    import contextlib
+    ctx = contextlib.nullcontext()
+    if a.backend == "accl" and a.heap_buckets:
+        ctx = torch.cuda.use_mem_pool(accl_b200.parallel.process_group.heap_mem_pool())
+    with ctx:
+        ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local] if a.backend == "nccl" else None, bucket_cap_mb=64,
+                                                        gradient_as_bucket_view=True)
     opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4)
     x = torch.randn(a.batch, a.width, device=dev, generator=torch.Generator(device=dev).manual_seed(rank))
 
@@ -67,7 +75,7 @@ def main():
     ok = bool(torch.allclose(chk, g))
     if rank == 0:
         nparam = sum(p.numel() for p in model.parameters())
-        row = dict(bench="ddp_step", backend=a.backend + ("+engine" if a.engine and a.backend == "accl" else ""), world=world, params=nparam,
+        row = dict(bench="ddp_step", backend=a.backend + ("+engine" if a.engine and a.backend == "accl" else "") + ("+heap_buckets" if a.heap_buckets else ""), world=world, params=nparam,
                    grad_mb=nparam * 4 / 2 ** 20, ms_per_step=float(t.item()), grads_agree=ok)
         print(json.dumps(row), flush=True)
         if a.out:

@@ -95,6 +95,8 @@ public:
   std::string debug_state();
   std::shared_ptr<BufferStorage> allocate(size_t bytes, bufferKind kind) override;
   std::shared_ptr<BufferStorage> wrap_host(void *host_ptr, size_t bytes) override;
+  // view of device memory that already lives inside this rank's heap (e.g. a torch tensor from the heap pool): zero-copy operand
+  std::shared_ptr<BufferStorage> wrap_device(void *dev_ptr, size_t bytes);
   void attach(int world_size, int local_rank) override;
 
   // ---- CUDA specifics
@@ -163,6 +165,10 @@ private:
 std::vector<std::unique_ptr<CudaDevice>> make_local_world(const std::vector<int> &devices, const CudaConfig &base);
 
 void bind_cuda(pybind11::module_ &m);
+
+// torch.cuda.MemPool over the heap (heap_pool.cpp): the backend that serves pool allocations of its CUDA device
+void heap_pool_attach(CudaDevice *d);
+void heap_pool_detach(CudaDevice *d);
 
 } // namespace cuda
 } // namespace accl

@@ -146,7 +146,8 @@ struct Ctrl {
   // stream id s (9..246, the reference's TDEST) is served by port s % N_STRM_PORTS, id 0 (no id) by port 0
   StrmPort strm[N_STRM_PORTS];
   uint32_t strm_err;               // sticky error bits raised by stream helper kernels
-  uint32_t strm_pad;
+  uint32_t clients_done;           // device-side clients (plugin kernels) that have finished, monotonic: the engine parks only
+                                   // once this has caught up with the host's count of clients launched (HostRing::clients)
   // ---- opt-in instrumentation (channel 0 only): where a call's time goes.  Read with CudaDevice::debug_state().
   unsigned long long dbg_calls;      // calls executed
   unsigned long long dbg_kernel_ns;  // sum of kernel body durations (run_work entry -> exit)

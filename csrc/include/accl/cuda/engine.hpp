@@ -24,7 +24,10 @@ public:
   void stop();
   // device-side clients (plugin kernels) are about to issue commands: keep the engine resident
   void pin();
-  void pin_resident(); // first device-side client: stay resident from now on (no host callback per launch)
+  // a kernel that issues commands itself is about to be launched: the engine stays resident until that kernel calls
+  // device::Command::client_done() (no host callback on the stream)
+  void client_begin();
+  void clients_reset(); // the control block was zeroed (soft reset)
   void unpin();
   struct Impl;
 

@@ -127,6 +127,14 @@ public:
                       cflags_, sflags_, src, 0, dst);
   }
   // non-blocking probe of an asynchronous call: true once retired (then *retcode holds the error word)
+  // Last thing a client kernel does (ONE thread, after its last finalize_call): tells the engine that this device-side
+  // client has finished, so the resident kernel may park again when idle.  The host side of the pair is
+  // Engine::client_begin(), called right before the client kernel is launched.
+  __device__ void client_done() {
+    __threadfence();
+    atomicAdd(&ctrl_->clients_done, 1u);
+  }
+
   __device__ bool test_call(Ticket ticket, uint32_t *retcode) {
     const unsigned long long v = dev::ld_acquire_sys(&ctrl_->cmd_status[(ticket - 1) % cuda::RING_SLOTS]);
     if ((v & 0xFFFFFFFFull) != (ticket & 0xFFFFFFFFull)) return false;

@@ -108,6 +108,23 @@ void bind_cuda(py::module_ &m) {
     auto *d = dynamic_cast<CudaDevice *>(a.device());
     if (d) d->drain();
   }, py::call_guard<py::gil_scoped_release>());
+  // zero-copy operands for memory that already lives in the heap (torch tensors from the heap pool)
+  m.def("cuda_wrap_device", [](ACCL &a, uintptr_t dev_ptr, size_t n, dataType t) {
+    auto *d = dynamic_cast<CudaDevice *>(a.device());
+    if (!d) throw std::runtime_error("not a CUDA backend");
+    const size_t bytes = n * dtype_bytes(t);
+    return std::unique_ptr<BaseBuffer>(new BaseBuffer(d->wrap_device(reinterpret_cast<void *>(dev_ptr), bytes), 0, bytes, t));
+  });
+  m.def("cuda_heap_range", [](ACCL &a) {
+    auto *d = dynamic_cast<CudaDevice *>(a.device());
+    if (!d) throw std::runtime_error("not a CUDA backend");
+    return std::make_pair(reinterpret_cast<uintptr_t>(d->heap().local()), d->heap().bytes());
+  });
+  m.def("cuda_heap_pool_attach", [](ACCL &a) {
+    auto *d = dynamic_cast<CudaDevice *>(a.device());
+    if (!d) throw std::runtime_error("not a CUDA backend");
+    heap_pool_attach(d);
+  });
   m.def("cuda_debug_state", [](ACCL &a) {
     auto *d = dynamic_cast<CudaDevice *>(a.device());
     if (!d) throw std::runtime_error("not a CUDA backend");

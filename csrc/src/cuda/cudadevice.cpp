@@ -67,9 +67,13 @@ public:
       if (!registered_) cudaGetLastError();
     }
   }
+  // a view of memory that already lives inside this rank's heap (torch tensors allocated from the heap pool): not
+  // owned, no host mirror unless somebody asks for one
+  CudaStorage(CudaDevice *d, size_t bytes, uint64_t heap_off)
+      : dev_(d), bytes_(bytes), kind_(bufferKind::p2p), off_(heap_off), owns_(false) {}
   ~CudaStorage() override {
     cudaSetDevice(dev_->device());
-    if (kind_ != bufferKind::host_only) {
+    if (kind_ != bufferKind::host_only && owns_) {
       // the engine may still be reading: drain the backend stream first
       cudaStreamSynchronize(dev_->stream());
       try {
@@ -121,6 +125,7 @@ private:
   size_t pinned_cap_ = 0;
   void *wrapped_ = nullptr;
   bool registered_ = false;
+  bool owns_ = true;
 };
 } // namespace
 
@@ -260,6 +265,7 @@ CudaDevice::CudaDevice(std::shared_ptr<Oob> oob, const CudaConfig &cfg) : oob_(s
 }
 
 CudaDevice::~CudaDevice() {
+  heap_pool_detach(this);
   cudaSetDevice(cfg_.device);
   engine_.reset();
   cudaStreamSynchronize(stream_);
@@ -386,6 +392,13 @@ std::shared_ptr<BufferStorage> CudaDevice::wrap_host(void *host_ptr, size_t byte
   return std::make_shared<CudaStorage>(this, bytes, bufferKind::device, host_ptr);
 }
 
+std::shared_ptr<BufferStorage> CudaDevice::wrap_device(void *dev_ptr, size_t bytes) {
+  const char *p = static_cast<const char *>(dev_ptr);
+  if (!heap_->contains(p) || !heap_->contains(p + (bytes ? bytes - 1 : 0)))
+    throw std::invalid_argument("wrap_device: the memory is not inside this rank's symmetric heap (allocate it from the heap pool)");
+  return std::make_shared<CudaStorage>(this, bytes, static_cast<uint64_t>(heap_->offset_of(p)));
+}
+
 // (re)build the eager slot area from the geometry in exchange memory
 void CudaDevice::setup_eager_area() {
   const uint32_t slot = std::max<uint32_t>(16, (shadow_[exchmem::EAGER_RX_BUF_SIZE / 4] + 15) & ~15u);
@@ -407,6 +420,7 @@ uint32_t CudaDevice::host_config(const CallDesc &d) {
     cudaStreamSynchronize(stream_);
     launch_reset_ctrl(world_, stream_);
     cudaStreamSynchronize(stream_);
+    if (engine_) engine_->clients_reset();
     for (auto &r : slot_owner_) r.reset();
     shadow_[exchmem::CFGRDY / 4] = 0;
     shadow_[exchmem::PKT_ENABLED / 4] = 0;

@@ -60,6 +60,7 @@ struct HostRing {
   volatile uint32_t pins;                // device-side clients active: do not park
   volatile uint32_t stop;                // host asks the engine to leave now
   volatile uint32_t idle_us;
+  volatile uint32_t clients;             // device-side client kernels launched so far (Ctrl::clients_done catches up)
 };
 
 __device__ __forceinline__ EngineArea *engine_area(const DevWorld &w) {
@@ -598,7 +599,7 @@ __device__ void engine_control(const DevWorld &w, HostRing *hr, int nworkers) {
       if (idle_ns > 20000ull) {
         const uint32_t stop = hr->stop;
         const bool idle_long = idle_us != 0 && idle_ns > static_cast<unsigned long long>(idle_us) * 1000ull;
-        if (stop || (idle_long && s_nactive == 0 && hr->pins == 0)) {
+        if (stop || (idle_long && s_nactive == 0 && hr->pins == 0 && hr->clients == dev::ld_acquire_sys(&me->clients_done))) {
           hr->state = ENG_EXITING;
           dev::fence_sc_sys();
           const bool pending = hr->submitted != s_host_fetched || dev::ld_acquire_sys(&me->cmd_ready[fetched % RING_SLOTS]) == fetched + 1;
@@ -809,7 +810,6 @@ struct Engine::Impl {
   cudaStream_t stream = nullptr;
   unsigned long long submitted = 0;
   int nworkers = 0;
-  bool resident = false;
   std::mutex m;
 };
 
@@ -896,14 +896,16 @@ void Engine::pin() {
   ensure_running_locked();
 }
 
-void Engine::pin_resident() {
+void Engine::client_begin() {
   std::lock_guard<std::mutex> g(impl_->m);
-  if (!impl_->resident) {
-    impl_->resident = true;
-    impl_->ring->pins = impl_->ring->pins + 1;
-    std::atomic_thread_fence(std::memory_order_seq_cst);
-  }
+  impl_->ring->clients = impl_->ring->clients + 1;
+  std::atomic_thread_fence(std::memory_order_seq_cst);
   ensure_running_locked();
+}
+
+void Engine::clients_reset() {
+  std::lock_guard<std::mutex> g(impl_->m);
+  impl_->ring->clients = 0;
 }
 
 void Engine::unpin() {

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(512) k_plugin_vadd_allreduce(DevWorld w, uint6
     st->finished = 0;
     __threadfence();
     *status = rc;
+    accl.client_done();
   }
 }
 
@@ -179,7 +180,7 @@ cudaError_t launch_vadd_allreduce(CudaDevice &dev, uint64_t x_off, uint64_t y_of
   chunk_elems = (chunk_elems + 3) & ~3u;
   while ((count + chunk_elems - 1) / chunk_elems > VADD_MAX_CHUNKS) chunk_elems *= 2;
   VaddState *st = reinterpret_cast<VaddState *>(dev.plugin_scratch(sizeof(VaddState)));
-  eng->pin_resident(); // a device-side client may issue commands at any time from now on: the engine does not park
+  eng->client_begin(); // the engine stays resident until the kernel's client_done()
   // the engine's CTAs stay resident next to this kernel: leave them (and a few spare) their SMs
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev.device());

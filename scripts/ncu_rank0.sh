@@ -4,7 +4,7 @@
 # a kernel that waits for its peers deadlocks; with one profiled rank (and a metric set that fits one pass, so nothing is
 # replayed) the peers simply wait a little longer.
 if [ "${LOCAL_RANK:-0}" = "0" ]; then
-  exec ncu --clock-control none -k regex:k_call --metrics "$NCU_METRICS" --csv --log-file "$NCU_LOG" python "$@"
+  exec ncu --replay-mode ${NCU_REPLAY:-kernel} --clock-control none -k regex:k_call --metrics "$NCU_METRICS" --csv --log-file "$NCU_LOG" python "$@"
 else
   exec python "$@"
 fi

@@ -138,3 +138,35 @@ def test_user_kernel_in_the_stream_path():
         assert torch.equal(d.host, torch.arange(n, dtype=torch.float32) + 100 * src + 1)
     A.run_cuda_ranks([0, 0], fn, dict(n_egr_rx_bufs=4, egr_rx_buf_size=16 << 10, max_egr_size=16 << 10,
                                           max_rndzv_size=1 << 26), heap_mb=64, max_ctas=4)
+
+
+def test_heap_mem_pool_tensors_are_zero_copy_operands():
+    """torch tensors allocated under `use_mem_pool(accl.heap_mem_pool())` live in the symmetric heap: TensorGroup takes
+    them without staging (this is how DDP's gradient buckets become zero-copy on the "accl" backend)."""
+    from accl_b200.parallel import TensorGroup
+    n = 1 << 18
+
+    def fn(a, r, w):
+        dev = torch.device("cuda", a.cuda_device)
+        g = TensorGroup(a)
+        pool = a.heap_mem_pool()
+        with torch.cuda.use_mem_pool(pool):
+            t = torch.full((n,), float(r + 1), device=dev)
+            u = torch.arange(n, device=dev, dtype=torch.float32) + r
+        plain = torch.full((n,), float(r + 1), device=dev)
+        assert a.heap_contains(t) and a.heap_contains(u) and not a.heap_contains(plain)
+        buf, staged = g._buffer_of(t, "s")
+        assert not staged and buf.dev.data_ptr() == t.data_ptr()
+        g.all_reduce(t)
+        g.all_reduce(u)
+        g.all_reduce(plain)
+        torch.cuda.current_stream().synchronize()
+        g.check(block=True)
+        s = float(sum(range(1, w + 1)))
+        assert torch.all(t == s) and torch.all(plain == s)
+        assert torch.equal(u.cpu(), torch.arange(n, dtype=torch.float32) * w + sum(range(w)))
+        assert not g._scratch or all(k[0] != "s" or v.length == n for k, v in g._scratch.items())  # only `plain` was staged
+        del t, u
+        return True
+
+    assert all(A.run_cuda_ranks(devices(2), fn, CFG, heap_mb=64, max_ctas=4))
