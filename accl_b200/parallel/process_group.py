@@ -29,12 +29,52 @@ def _done(result):
     return _create_work_from_future(fut)
 
 
+def _cuda_device_of(x):
+    if isinstance(x, torch.Tensor):
+        return x.device if x.is_cuda else None
+    if isinstance(x, (list, tuple)):
+        for y in x:
+            d = _cuda_device_of(y)
+            if d is not None:
+                return d
+    return None
+
+
 class AcclProcessGroup(dist.ProcessGroup):
     def __init__(self, rank, world_size, accl, comm_id=0):
         super().__init__(rank, world_size)
         self._rank, self._world = rank, world_size
         self.accl = accl
         self.group = TensorGroup(accl, comm_id)
+        self._comm_stream = None   # CUDA: collectives run here so that they overlap the caller's compute (like NCCL's)
+        self._overlap = os.environ.get("ACCL_PG_OVERLAP", "1") not in ("", "0")
+
+    def _join(self):
+        """Ops that run on the caller's stream share staging buffers with the communication stream: order after it."""
+        if self._comm_stream is not None:
+            torch.cuda.current_stream(self._comm_stream.device).wait_stream(self._comm_stream)
+
+    def _run(self, tensors, fn):
+        """Run `fn` (which issues the collective and any staging copies) and return its Work.  CUDA tensors: on this
+        group's communication stream, ordered after what the caller has queued so far; the Work's future carries the
+        completion event, so `work.wait()` / `fut.then(...)` order the caller's stream after the collective without
+        blocking the host — DDP's backward keeps running while a bucket is being reduced."""
+        dev = _cuda_device_of(tensors) if self.accl.is_cuda else None
+        if dev is None or not self._overlap:
+            fn()
+            return _done(tensors)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=dev, priority=-1)
+        cs = self._comm_stream
+        cs.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cs):
+            fn()
+            fut = Future(devices=[dev])
+            fut.set_result(tensors)          # records the completion event on the communication stream
+        for t in (tensors if isinstance(tensors, (list, tuple)) else [tensors]):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(cs)
+        return _create_work_from_future(fut)
 
     # -- identity ------------------------------------------------------------
     def getBackendName(self):
@@ -65,20 +105,24 @@ class AcclProcessGroup(dist.ProcessGroup):
     # -- collectives ----------------------------------------------------------------
     def allreduce(self, tensor_list, opts=AllreduceOptions()):
         fn, post = self._op(opts)
-        for t in tensor_list:
-            self.group.all_reduce(t, fn)
-            self._finish(t, post)
-        return _done(tensor_list)
+
+        def go():
+            for t in tensor_list:
+                self.group.all_reduce(t, fn)
+                self._finish(t, post)
+        return self._run(tensor_list, go)
 
     def allreduce_coalesced(self, tensor_list, opts=AllreduceCoalescedOptions()):
         return self.allreduce(tensor_list, opts)
 
     def broadcast(self, tensor_list, opts=BroadcastOptions()):
-        for t in tensor_list:
-            self.group.broadcast(t, opts.rootRank)
-        return _done(tensor_list)
+        def go():
+            for t in tensor_list:
+                self.group.broadcast(t, opts.rootRank)
+        return self._run(tensor_list, go)
 
     def reduce(self, tensor_list, opts=ReduceOptions()):
+        self._join()
         fn, post = self._op(opts)
         for t in tensor_list:
             n = t.numel()
@@ -94,10 +138,10 @@ class AcclProcessGroup(dist.ProcessGroup):
         return _done(tensor_list)
 
     def _allgather_base(self, output_tensor, input_tensor, opts=AllgatherOptions()):
-        self.group.all_gather_into_tensor(output_tensor, input_tensor.contiguous())
-        return _done(output_tensor)
+        return self._run([output_tensor, input_tensor], lambda: self.group.all_gather_into_tensor(output_tensor, input_tensor.contiguous()))
 
     def allgather(self, output_tensors, input_tensor, opts=AllgatherOptions()):
+        self._join()
         for outs, inp in zip(output_tensors, input_tensor):
             flat = torch.empty(self._world * inp.numel(), dtype=inp.dtype, device=inp.device)
             self.group.all_gather_into_tensor(flat, inp.contiguous())
@@ -107,32 +151,36 @@ class AcclProcessGroup(dist.ProcessGroup):
 
     def allgather_into_tensor_coalesced(self, output_tensor_list, input_tensor_list, opts=AllgatherOptions()):
         for o, i in zip(output_tensor_list, input_tensor_list):
-            self._allgather_base(o, i, opts)
+            self._allgather_base(o, i, opts).wait()   # (orders the caller's stream after the communication stream)
         return _done(output_tensor_list)
 
     def _reduce_scatter_base(self, output_tensor, input_tensor, opts=ReduceScatterOptions()):
         fn, post = self._op(opts)
-        self.group.reduce_scatter_tensor(output_tensor, input_tensor.contiguous(), fn)
-        self._finish(output_tensor, post)
-        return _done(output_tensor)
+
+        def go():
+            self.group.reduce_scatter_tensor(output_tensor, input_tensor.contiguous(), fn)
+            self._finish(output_tensor, post)
+        return self._run([output_tensor, input_tensor], go)
 
     def reduce_scatter(self, output_tensors, scatter_lists, opts=ReduceScatterOptions()):
         for out, parts in zip(output_tensors, scatter_lists):
-            self._reduce_scatter_base(out, torch.cat([p.reshape(-1) for p in parts]), opts)
+            self._reduce_scatter_base(out, torch.cat([p.reshape(-1) for p in parts]), opts).wait()
         return _done(output_tensors)
 
     def reduce_scatter_tensor_coalesced(self, output_tensors, input_tensors, opts=ReduceScatterOptions()):
         for o, i in zip(output_tensors, input_tensors):
-            self._reduce_scatter_base(o, i, opts)
+            self._reduce_scatter_base(o, i, opts).wait()
         return _done(output_tensors)
 
     def alltoall_base(self, output_buffer, input_buffer, output_split_sizes, input_split_sizes, opts=AllToAllOptions()):
+        self._join()
         if output_split_sizes or input_split_sizes:
             raise NotImplementedError("accl backend: all_to_all_single with uneven splits")
         self.group.all_to_all_single(output_buffer, input_buffer.contiguous())
         return _done(output_buffer)
 
     def alltoall(self, output_tensor_list, input_tensor_list, opts=AllToAllOptions()):
+        self._join()
         inp = torch.cat([t.reshape(-1) for t in input_tensor_list])
         out = torch.empty_like(inp)
         self.group.all_to_all_single(out, inp)
@@ -141,6 +189,7 @@ class AcclProcessGroup(dist.ProcessGroup):
         return _done(output_tensor_list)
 
     def gather(self, output_tensors, input_tensors, opts=GatherOptions()):
+        self._join()
         inp = input_tensors[0].contiguous()
         n = inp.numel()
         sb, _ = self.group._buffer_of(inp.view(-1), "s")
@@ -154,6 +203,7 @@ class AcclProcessGroup(dist.ProcessGroup):
         return _done(output_tensors)
 
     def scatter(self, output_tensors, input_tensors, opts=ScatterOptions()):
+        self._join()
         out = output_tensors[0]
         n = out.numel()
         sb = self.accl.create_buffer(n * self._world, out.dtype)
@@ -166,17 +216,20 @@ class AcclProcessGroup(dist.ProcessGroup):
         return _done(output_tensors)
 
     def barrier(self, opts=BarrierOptions()):
+        self._join()
         self.group.barrier()
         return _done(None)
 
     # -- point to point ----------------------------------------------------------------
     def send(self, tensors, dst, tag=0):
+        self._join()
         reqs = [self.group.send(t.contiguous(), dst, tag) for t in tensors]
         for r in reqs:      # asynchronous issue (a rendezvous send completes when the peer has posted its recv)
             r.wait()
         return _done(None)
 
     def recv(self, tensors, src, tag=0):
+        self._join()
         for t in tensors:
             self.group.recv(t, src, tag)
         return _done(tensors)

@@ -42,15 +42,23 @@ def main():
         per[r["Process ID"]][int(r["ID"])][r["Metric Name"]] = (r["Metric Value"], r["Metric Unit"])
     pids = sorted(per)
     calls = plan["calls"]
-    print(f"# ncu: collective kernels on {plan['world']} x B200 (application replay, `--clock-control none`)\n")
+    print(f"# ncu: collective kernels on {plan['world']} x B200 (one rank under ncu, single-pass metric set, `--clock-control none`)\n")
     print(f"`{plan['describe']}`\n")
-    print("One `k_call` launch per call; rows are the second repetition of every call (the first warms up).  NVLink columns are this GPU's "
-          "`nvltx__bytes.sum` / `nvlrx__bytes.sum` (all 18 links, headers included; `user` = payload only); rates = bytes / kernel time.\n")
-    print("| call | size | rank (pid) | grid | kernel us | NVLink tx MB (user) | NVLink rx MB (user) | tx GB/s | rx GB/s | DRAM rd MB | DRAM wr MB | SM busy % |")
-    print("|---|---|---|---|---|---|---|---|---|---|---|---|")
+    have_nvl = any("nvltx__bytes.sum" in m for pid in pids for m in per[pid].values())
+    print("One `k_call` launch per call; rows are the second repetition of every call (the first warms up); the profiled rank runs "
+          "under ncu with a metric set that fits one pass (nothing is replayed), its peers run unprofiled.  "
+          "Rates = bytes / kernel time." + ("" if have_nvl else "  NVLink byte counts for the same calls: `profiles/nvlink_traffic_*.jsonl` "
+                                            "(`nvidia-smi nvlink -gt d` deltas; ncu needs a second pass for the nvl* counters, which a "
+                                            "multi-rank kernel cannot be replayed for).") + "\n")
+    hdr = ["call", "size", "grid", "kernel us", "algorithm bytes / kernel time GB/s"]
+    if have_nvl:
+        hdr += ["NVLink tx MB", "NVLink rx MB", "tx GB/s", "rx GB/s"]
+    hdr += ["DRAM read MB", "DRAM write MB", "DRAM GB/s"]
+    print("| " + " | ".join(hdr) + " |")
+    print("|" + "---|" * len(hdr))
+    P = plan["world"]
     for pi, pid in enumerate(pids):
         ks = [per[pid][k] for k in sorted(per[pid])]
-        # the trailing barrier (and anything else after the planned calls) is ignored
         for i, c in enumerate(calls):
             if i >= len(ks) or c["rep"] != 1:
                 continue
@@ -59,10 +67,17 @@ def main():
             def b(name):
                 return to_bytes(*m[name]) if name in m else float("nan")
             t = to_us(*m["gpu__time_duration.sum"])
-            tx, rx, txu, rxu = b("nvltx__bytes.sum"), b("nvlrx__bytes.sum"), b("nvltx__bytes_data_user.sum"), b("nvlrx__bytes_data_user.sum")
-            print(f"| {c['op']} | {human(c['bytes'])} | {pi} ({pid}) | {m.get('launch__grid_size', ('?', ''))[0]} | {t:.1f} | {tx / 1e6:.2f} ({txu / 1e6:.2f}) | "
-                  f"{rx / 1e6:.2f} ({rxu / 1e6:.2f}) | {tx / t * 1e-3:.0f} | {rx / t * 1e-3:.0f} | {b('dram__bytes_read.sum') / 1e6:.1f} | "
-                  f"{b('dram__bytes_write.sum') / 1e6:.1f} | {float(m.get('sm__throughput.avg.pct_of_peak_sustained_elapsed', ('nan', ''))[0]):.1f} |")
+            # bytes this rank has to send (= receive) for the call, the quantity the bus-bandwidth convention is built on
+            nb = c["bytes"]
+            wire = {"allreduce": 2.0 * nb * (P - 1) / P, "allreduce bf16 wire": nb * (P - 1) / P, "allgather": nb * (P - 1) / P,
+                    "reduce_scatter": nb * (P - 1) / P, "bcast": nb, "reduce": nb}.get(c["op"], nb)
+            row = [c["op"], human(nb), m.get("launch__grid_size", ("?", ""))[0], f"{t:.1f}", f"{wire / t * 1e-3:.0f}"]
+            if have_nvl:
+                tx, rx = b("nvltx__bytes.sum"), b("nvlrx__bytes.sum")
+                row += [f"{tx / 1e6:.2f}", f"{rx / 1e6:.2f}", f"{tx / t * 1e-3:.0f}", f"{rx / t * 1e-3:.0f}"]
+            rd, wr = b("dram__bytes_read.sum"), b("dram__bytes_write.sum")
+            row += [f"{rd / 1e6:.1f}", f"{wr / 1e6:.1f}", f"{(rd + wr) / t * 1e-3:.0f}"]
+            print("| " + " | ".join(row) + " |")
     print()
 
 
