@@ -19,24 +19,31 @@ def close(a, b, rtol, atol):
     return torch.allclose(a.cpu().double(), b.cpu().double(), rtol=rtol, atol=atol)
 
 
+@pytest.mark.parametrize("variant,out_dtype", [(0, torch.bfloat16), (1, torch.bfloat16), (2, torch.bfloat16), (2, torch.float32),
+                                               (1, torch.float32)])
 @pytest.mark.parametrize("world", [1, 2])
-def test_gemm_reduce_scatter_matches_fp32_reference(world):
-    M, N, K = 256 * world, 512, 256
+def test_gemm_reduce_scatter_matches_fp32_reference(world, variant, out_dtype):
+    """Both tcgen05 kernels (one CTA per 128 x 256 tile; CTA pair, cta_group::2, per 256 x 256 tile), bf16 and fp32 shards,
+    against an fp32 matmul of the same bf16 operands summed over ranks in fp32."""
+    M, N, K = 512 * world, 512, 320   # several tiles per rank, a K that is not a multiple of the stage depth
 
     def fn(a, r, w):
         g = torch.Generator().manual_seed(100 + r)
         x = (torch.randn(M, K, generator=g) * 0.5).bfloat16().cuda(a.cuda_device)
         wt = (torch.randn(N, K, generator=g) * 0.5).bfloat16().cuda(a.cuda_device)
-        out = gemm_reduce_scatter(a, x, wt)
+        out = gemm_reduce_scatter(a, x, wt, variant=variant, out_dtype=out_dtype)
         torch.cuda.current_stream().synchronize()
+        assert out.dev.dtype == out_dtype
         return out.dev.view(M // w, N).float().cpu(), x.float().cpu(), wt.float().cpu()
 
     res = A.run_cuda_ranks(devices(world), fn, CFG, heap_mb=64, max_ctas=4)
     full = sum(x @ wt.t() for _, x, wt in res)  # fp32 reference of the same op
     for r, (shard, _, _) in enumerate(res):
         ref = full[r * (M // world):(r + 1) * (M // world)]
-        # bf16 output, bf16 adds of `world` partials
-        assert close(shard, ref, 2e-2, 2e-1 * world), (r, (shard - ref).abs().max())
+        if out_dtype == torch.float32:
+            assert close(shard, ref, 1e-4, 1e-3), (r, (shard - ref).abs().max())    # fp32 accumulation end to end
+        else:
+            assert close(shard, ref, 2e-2, 2e-1 * world), (r, (shard - ref).abs().max())  # bf16 output, bf16 adds of `world` partials
 
 
 def test_engine_mode_collectives():
