@@ -501,7 +501,7 @@ def bind_to_gpu_numa_node(device):
 
 
 def cuda_rank(rank=None, world_size=None, device=None, addr=None, port=None, heap_mb=1024, multicast=True,
-              max_ctas=32, engine=False, nvls_min_ranks=3, oneshot_kb=2048, nvls_ops=-1, **extra):
+              max_ctas=128, engine=False, nvls_min_ranks=3, oneshot_kb=2048, nvls_ops=-1, **extra):
     """One rank per process (torchrun): RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT."""
     _prepare_cuda_env()
     rank = int(os.environ.get("RANK", 0)) if rank is None else rank

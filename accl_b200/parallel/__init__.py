@@ -41,6 +41,8 @@ def init_from_env(backend=None, **kw):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         if "engine" not in kw and os.environ.get("ACCL_PG_ENGINE") is not None:
             kw["engine"] = os.environ["ACCL_PG_ENGINE"] not in ("", "0")
+        if "max_ctas" not in kw and os.environ.get("ACCL_MAX_CTAS"):
+            kw["max_ctas"] = int(os.environ["ACCL_MAX_CTAS"])  # channel cap (default 128; the planner sizes every call)
         if "heap_mb" not in kw and os.environ.get("ACCL_HEAP_MB"):
             kw["heap_mb"] = int(os.environ["ACCL_HEAP_MB"])   # symmetric heap per rank (default 1024)
         acc = cuda_rank(**kw)

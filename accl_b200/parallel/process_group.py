@@ -261,7 +261,8 @@ def _create(opts, pg_options=None):
         assert accl.rank == rank and accl.world == size, "accl backend: rank / world size disagree with init_process_group"
         _primary["accl"] = accl
         _primary["ranks"] = accl.generate_ranks(size)
-        return AcclProcessGroup(rank, size, accl)
+        _primary["pg"] = AcclProcessGroup(rank, size, accl)
+        return _primary["pg"]
     accl = _primary["accl"]
     if ranks == list(range(accl.world)):
         # another world-sized group: its own communicator (and bank) so it can be used concurrently

@@ -42,10 +42,12 @@ def main():
         layers += [torch.nn.Linear(a.width, a.width), torch.nn.GELU()]
     model = torch.nn.Sequential(*layers).to(dev)
     import contextlib
-    ctx = contextlib.nullcontext()
-    if a.backend == "accl" and a.heap_buckets:
-        ctx = torch.cuda.use_mem_pool(accl_b200.parallel.process_group.heap_mem_pool())
-    with ctx:
+    def ctx():
+        if a.backend == "accl" and a.heap_buckets:
+            return torch.cuda.use_mem_pool(accl_b200.parallel.process_group.heap_mem_pool())
+        return contextlib.nullcontext()
+
+    with ctx():
         ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local] if a.backend == "nccl" else None, bucket_cap_mb=64,
                                                         gradient_as_bucket_view=True)
     opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4)
@@ -56,8 +58,14 @@ def main():
         ddp(x).square().mean().backward()
         opt.step()
 
+    # DDP rebuilds its buckets (in gradient-ready order) at the start of the second forward: keep the warm-up forwards
+    # inside the pool so that the rebuilt buckets are heap-resident too
     for _ in range(3):
-        step()
+        opt.zero_grad(set_to_none=True)
+        with ctx():
+            out = ddp(x)
+        out.square().mean().backward()
+        opt.step()
     torch.cuda.synchronize()
     dist.barrier()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -77,6 +85,10 @@ def main():
         nparam = sum(p.numel() for p in model.parameters())
         row = dict(bench="ddp_step", backend=a.backend + ("+engine" if a.engine and a.backend == "accl" else "") + ("+heap_buckets" if a.heap_buckets else ""), world=world, params=nparam,
                    grad_mb=nparam * 4 / 2 ** 20, ms_per_step=float(t.item()), grads_agree=ok)
+        if a.backend == "accl":
+            g = accl_b200.parallel.process_group._primary["pg"].group
+            row["staged_mb"] = sum(b.nbytes for b in g._scratch.values()) / 2 ** 20   # 0 when every bucket was a zero-copy operand
+            row["zero_copy_tensors"] = len(g._wrapped)
         print(json.dumps(row), flush=True)
         if a.out:
             os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
