@@ -361,6 +361,11 @@ class Accl:
     def set_max_rendezvous_msg_size(self, value):
         self._a.set_max_rendezvous_msg_size(value)
 
+    def set_one_hop_schedules(self, on=True):
+        """Emulator: execute the schedules of the B200 backend (one-hop all-gather / reduce-scatter / one-shot and
+        two-shot all-reduce, flat rooted collectives) instead of the reference's rings and trees.  Same value on every rank."""
+        self._a.set_one_hop_schedules(bool(on))
+
     def dump_communicator(self):
         return self._a.dump_communicator()
 

@@ -161,6 +161,7 @@ PYBIND11_MODULE(_C, m) {
       }, py::keep_alive<0, 1>())
       .def("set_timeout", [](ACCL &a, unsigned v) { a.free_request(a.set_timeout(v)); }, gil_release())
       .def("set_max_eager_msg_size", [](ACCL &a, unsigned v) { a.free_request(a.set_max_eager_msg_size(v)); }, gil_release())
+      .def("set_one_hop_schedules", &ACCL::set_one_hop_schedules)
       .def("set_max_rendezvous_msg_size", [](ACCL &a, unsigned v) { a.free_request(a.set_max_rendezvous_msg_size(v)); }, gil_release())
       .def("nop", [](ACCL &a, bool async_) { return wrap(a, a.nop(async_)); }, py::arg("run_async") = false, gil_release())
       .def("send", [](ACCL &a, BaseBuffer &b, unsigned count, unsigned dst, unsigned tag, unsigned comm, bool from_fpga,

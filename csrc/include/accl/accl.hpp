@@ -47,6 +47,11 @@ public:
   ACCLRequest *set_timeout(unsigned int value, bool run_async = false, std::vector<ACCLRequest *> waitfor = {});
   ACCLRequest *set_max_eager_msg_size(unsigned int value, bool run_async = false, std::vector<ACCLRequest *> waitfor = {});
   ACCLRequest *set_max_rendezvous_msg_size(unsigned int value, bool run_async = false, std::vector<ACCLRequest *> waitfor = {});
+  // Emulator: run all-gather / reduce-scatter / all-reduce as one-hop exchanges and the rooted collectives in their flat
+  // forms — the schedules the B200 backend executes on an NVSwitch domain — instead of the reference's rings and trees.
+  // Set it identically on every rank (before or after initialize).  The CUDA backend always runs one-hop schedules.
+  void set_one_hop_schedules(bool on);
+  bool one_hop_schedules() const { return one_hop_schedules_; }
   ACCLRequest *nop(bool run_async = false, std::vector<ACCLRequest *> waitfor = {});
 
   // ---- primitives
@@ -198,6 +203,7 @@ private:
   void setup_eager_rx_buffers(size_t n_egr_rx_bufs, addr_t egr_rx_buf_size);
   void setup_rendezvous_spare_buffers(addr_t rndzv_spare_buf_size);
   void configure_tuning_parameters();
+  bool one_hop_schedules_ = false;
   void configure_communicator(const std::vector<rank_t> &ranks, int local_rank);
   void check_return_value(const std::string &function_name, ACCLRequest *request);
   void prepare_call(CCLO::Options &options);

@@ -42,6 +42,8 @@ constexpr uint32_t NUM_COMMUNICATORS = 0x03C;
 constexpr uint32_t NUM_ARITHCFG = 0x040;
 constexpr uint32_t PKT_ENABLED = 0x044;     // data plane enabled (cfgFunc::enable_pkt)
 constexpr uint32_t SPARE_BUF_SIZE = 0x048;  // bytes of each rendezvous scratch buffer
+constexpr uint32_t ONE_HOP_SCHEDULES = 0x04C; // emulator: 1 = all-gather / reduce-scatter / all-reduce as one-hop exchanges and
+                                              // rooted collectives in their flat forms (the schedules the B200 backend runs)
 constexpr uint32_t SPARE_BUF_BASE = 0x050;  // 3 x {addr lo, addr hi}
 constexpr uint32_t NUM_SPARE_BUFS = 3;
 

@@ -11,6 +11,7 @@
 // saved step.  The code below is an independent formulation of those
 // behaviours (resumable `Steps` instead of current_step gotos).
 #include <algorithm>
+#include <atomic>
 
 #include "accl/common.hpp"
 #include "engine_ctx.hpp"
@@ -452,7 +453,7 @@ uint32_t Engine::fw_bcast(EmuCall &c) {
     return egr_recv(x, root, imm(x.a0, x.op0_c()), x.count, x.tag, x.res_stream(), x.stream_id());
   }
   // ---- rendezvous
-  const uint32_t flat_max = read_exch(exchmem::BCAST_FLAT_TREE_MAX_RANKS);
+  const uint32_t flat_max = read_exch(exchmem::ONE_HOP_SCHEDULES) ? ~0u : read_exch(exchmem::BCAST_FLAT_TREE_MAX_RANKS);
   Steps st(c.step);
   if (P <= flat_max) {
     // flat tree: peers announce their buffers, root serves them in arrival order
@@ -556,6 +557,20 @@ uint32_t Engine::fw_gather(EmuCall &c) {
   FW_DECODE(x);
   const uint32_t P = x.comm.size, me = x.comm.local_rank, root = x.root;
   const uint64_t slot_bytes = x.op_bytes(x.res_c(), x.count);
+  if (x.eager && one_hop(x, 0)) {
+    // fan-in: everybody sends its block straight to the root
+    if (me != root) return egr_send(x, root, imm(x.a0), x.count, x.tag, false, 0);
+    Move m;
+    m.op0 = imm(x.a0);
+    m.res = imm(x.a2 + root * slot_bytes);
+    m.count = x.count;
+    uint32_t err = execute(x, m);
+    for (uint32_t k = 1; k < P && !err; ++k) {
+      const uint32_t from = (root + P - k) % P;
+      err |= egr_recv(x, from, imm(x.a2 + from * slot_bytes), x.count, x.tag, false, 0);
+    }
+    return err;
+  }
   if (x.eager) {
     // daisy chain towards the root: r -> r+1 -> ... -> root.  A rank first
     // injects its own block, then relays the blocks of the ranks behind it.
@@ -609,7 +624,7 @@ uint32_t Engine::fw_gather(EmuCall &c) {
     });
     if (err) return err;
     uint32_t fanin = P - 1;
-    if (x.count * x.ubytes() > read_exch(exchmem::GATHER_FLAT_TREE_MAX_COUNT))
+    if (x.count * x.ubytes() > read_exch(exchmem::GATHER_FLAT_TREE_MAX_COUNT) && !read_exch(exchmem::ONE_HOP_SCHEDULES))
       fanin = std::max(1u, read_exch(exchmem::GATHER_FLAT_TREE_MAX_FANIN));
     // peers are admitted in rank order, `fanin` outstanding at a time:
     // c.mask = peers whose completion has been collected; the admission
@@ -638,6 +653,124 @@ uint32_t Engine::fw_gather(EmuCall &c) {
   return rndzv_write(x, root, x.a0, vaddr, x.count, x.tag);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One-hop schedules (exchmem::ONE_HOP_SCHEDULES != 0): the exchanges the B200 backend runs on an NVSwitch domain,
+// where every peer is one hop away — all-gather: every rank delivers its block straight to every peer;
+// reduce-scatter: every rank delivers block q to its owner q, the owner reduces; all-reduce: everybody-sends-everything
+// while small (or when the count does not split), reduce-scatter + all-gather above (plan.hpp: WF_ONESHOT /
+// two-shot); rooted collectives take their flat forms.  Same primitives as the reference-style algorithms below
+// (eager sends into RX buffers; address note, one-sided write, completion note), so the CPU suite exercises the
+// data flow and the in-place hazards of the GPU schedules.  Uncompressed, non-stream calls only (as on the GPU, where
+// compressed / stream calls take other paths); everything else keeps the ring / tree forms.
+namespace {
+std::atomic<uint64_t> g_one_hop_dispatches{0}; // process-wide statistic (ranks as threads share it): shown by debug_state
+}
+uint64_t one_hop_dispatches() { return g_one_hop_dispatches.load(); }
+
+bool Engine::one_hop(const Ctx &x, uint64_t landing_bytes) {
+  if (!read_exch(exchmem::ONE_HOP_SCHEDULES) || x.cflags || x.sflags || x.comm.size < 2) return false;
+  if (!x.eager && landing_bytes > x.spare_size) return false;
+  if (x.call && x.call->step == 0 && x.call->mask == 0) g_one_hop_dispatches.fetch_add(1); // first attempt of the call
+  return true;
+}
+
+// Every rank delivers `count` elements at own_block to slot `me` of every peer's dst_base (slots of blk_bytes).
+// step / mask: resumable state of a parked call (mask bits 0-15: peers written, bits 16-20: completions collected).
+uint32_t Engine::onehop_gather(Ctx &x, uint32_t &step, uint32_t &mask, uint64_t own_block, uint64_t dst_base, uint64_t blk_bytes,
+                               uint32_t count) {
+  const uint32_t P = x.comm.size, me = x.comm.local_rank;
+  uint32_t err = 0;
+  if (x.eager) {
+    for (uint32_t k = 1; k < P && !err; ++k) err |= egr_send(x, (me + k) % P, imm(own_block), count, x.tag, false, 0);
+    for (uint32_t k = 1; k < P && !err; ++k) {
+      const uint32_t from = (me + P - k) % P;
+      err |= egr_recv(x, from, imm(dst_base + from * blk_bytes), count, x.tag, false, 0);
+    }
+    return err;
+  }
+  Steps st(step);
+  st([&] {
+    for (uint32_t r = 0; r < P; ++r)
+      if (r != me) rndzv_post_addr(x, r, dst_base + r * blk_bytes, count * x.ubytes(), x.tag);
+    return true;
+  });
+  const uint32_t all = ((1u << P) - 1) & ~(1u << me);
+  while ((mask & 0xFFFFu) != all) {
+    uint32_t to = 0;
+    uint64_t vaddr = 0;
+    if (!rndzv_take_any_addr(x, (mask & 0xFFFFu) | (1u << me), x.tag, to, vaddr)) return NOT_READY_ERROR;
+    err = rndzv_write(x, to, own_block, vaddr, count, x.tag);
+    if (err) return err;
+    mask |= 1u << to;
+  }
+  while (((mask >> 16) & 0x1Fu) != P - 1) {
+    uint32_t from = 0;
+    if (!rndzv_take_any_done(x, 1u << me, x.tag, from)) return NOT_READY_ERROR;
+    mask += 1u << 16;
+  }
+  return 0;
+}
+
+// Every rank q contributes `count` elements at src_base + owner * src_stride to every owner (src_stride 0: the same
+// vector to everybody — one-shot all-reduce); this rank reduces the P contributions for itself into dst.
+// Rendezvous form: contributions land one at a time in scratch 0 and are folded ping-pong through scratch 1 / 2; the
+// fold that writes dst waits until this rank has delivered all of its own contributions (dst may alias the source).
+uint32_t Engine::onehop_reduce(Ctx &x, uint32_t &step, uint32_t &mask, uint64_t src_base, uint64_t src_stride, uint64_t dst,
+                               uint32_t count) {
+  const uint32_t P = x.comm.size, me = x.comm.local_rank;
+  uint32_t err = 0;
+  if (x.eager) {
+    for (uint32_t k = 1; k < P && !err; ++k) {
+      const uint32_t to = (me + k) % P;
+      err |= egr_send(x, to, imm(src_base + to * src_stride), count, x.tag, false, 0);
+    }
+    Operand acc = imm(src_base + me * src_stride);
+    for (uint32_t k = 1; k < P && !err; ++k) {
+      err |= egr_recv_reduce(x, (me + P - k) % P, acc, imm(dst), count, x.tag);
+      acc = imm(dst);
+    }
+    return err;
+  }
+  // step: 2 * contributions folded + (address for the next one posted); mask bits 0-15: owners written to
+  const uint32_t all = ((1u << P) - 1) & ~(1u << me);
+  for (;;) {
+    bool progressed = false;
+    while ((mask & 0xFFFFu) != all) { // sender role: serve whichever owner has exposed its landing buffer
+      uint32_t to = 0;
+      uint64_t vaddr = 0;
+      if (!rndzv_take_any_addr(x, (mask & 0xFFFFu) | (1u << me), x.tag, to, vaddr)) break;
+      err = rndzv_write(x, to, src_base + to * src_stride, vaddr, count, x.tag);
+      if (err) return err;
+      mask |= 1u << to;
+      progressed = true;
+    }
+    const uint32_t served = step >> 1;
+    if (served < P - 1) { // owner role
+      const uint32_t from = (me + P - 1 - served) % P;
+      if (!(step & 1u)) {
+        rndzv_post_addr(x, from, x.spare[0], count * x.ubytes(), x.tag);
+        step |= 1u;
+        progressed = true;
+      }
+      const bool last = served + 1 == P - 1;
+      if ((!last || (mask & 0xFFFFu) == all) && rndzv_take_done(x, from, x.tag)) {
+        Move m;
+        m.op0 = imm(served == 0 ? src_base + me * src_stride : x.spare[1 + (served & 1)]);
+        m.op1 = imm(x.spare[0]);
+        m.res = imm(last ? dst : x.spare[1 + ((served + 1) & 1)]);
+        m.count = count;
+        m.func = x.fn();
+        err = execute(x, m);
+        if (err) return err;
+        step = (served + 1) << 1;
+        progressed = true;
+      }
+    }
+    if ((step >> 1) == P - 1 && (mask & 0xFFFFu) == all) return 0;
+    if (!progressed) return NOT_READY_ERROR;
+  }
+}
+
 // --------------------------------------------------------------- allgather
 uint32_t Engine::fw_allgather(EmuCall &c) {
   FW_DECODE(x);
@@ -645,6 +778,21 @@ uint32_t Engine::fw_allgather(EmuCall &c) {
   const uint64_t slot_bytes = x.op_bytes(x.res_c(), x.count);
   const uint32_t next = (me + 1) % P, prev = (me + P - 1) % P;
   uint32_t err = 0;
+  if (one_hop(x, 0)) {
+    if (!(c.mask & 0x80000000u)) { // own block into place, once
+      Move m;
+      m.op0 = imm(x.a0);
+      m.res = imm(x.a2 + me * slot_bytes);
+      m.count = x.count;
+      err = execute(x, m);
+      if (err) return err;
+      c.mask |= 0x80000000u;
+    }
+    uint32_t mask = c.mask & 0x7FFFFFFFu;
+    err = onehop_gather(x, c.step, mask, x.a2 + me * slot_bytes, x.a2, slot_bytes, x.count);
+    c.mask = mask | 0x80000000u;
+    return err;
+  }
   if (x.eager) {
     Move m; // own block into place
     m.op0 = x.op0_stream() ? stream_op() : imm(x.a0, x.op0_c());
@@ -702,6 +850,17 @@ uint32_t Engine::fw_reduce(EmuCall &c) {
     m.count = x.count;
     return execute(x, m);
   }
+  if (x.eager && one_hop(x, 0)) {
+    // fan-in: everybody sends to the root, which folds the contributions in as they are matched
+    if (me != root) return egr_send(x, root, src, x.count, x.tag, false, 0);
+    uint32_t err = 0;
+    Operand acc = src;
+    for (uint32_t k = 1; k < P && !err; ++k) {
+      err |= egr_recv_reduce(x, (root + P - k) % P, acc, dst, x.count, x.tag);
+      acc = dst;
+    }
+    return err;
+  }
   if (x.eager) {
     // chain root+1 -> root+2 -> ... -> root, each hop folds in its own data
     const uint32_t next = (me + 1) % P, prev = (me + P - 1) % P;
@@ -713,7 +872,7 @@ uint32_t Engine::fw_reduce(EmuCall &c) {
   const uint32_t chunk_max = std::max(1u, x.spare_size / std::max(1u, x.ubytes()));
   const uint32_t flat_ranks = read_exch(exchmem::REDUCE_FLAT_TREE_MAX_RANKS);
   const uint32_t flat_count = read_exch(exchmem::REDUCE_FLAT_TREE_MAX_COUNT);
-  const bool flat = P <= flat_ranks || x.count * x.ubytes() <= flat_count;
+  const bool flat = P <= flat_ranks || x.count * x.ubytes() <= flat_count || read_exch(exchmem::ONE_HOP_SCHEDULES);
   Steps st(c.step);
   uint32_t err = 0;
   for (uint32_t off = 0; off < x.count; off += chunk_max) {
@@ -809,6 +968,7 @@ uint32_t Engine::fw_reduce_scatter(EmuCall &c) {
     m.count = x.count;
     return execute(x, m);
   }
+  if (one_hop(x, blk)) return onehop_reduce(x, c.step, c.mask, x.a0, blk, x.a2, x.count);
   if (!x.eager) {
     // rendezvous: reduce count*P to rank 0 (in scratch-sized chunks), then scatter.
     // Both phases are resumable sub-calls sharing this call's step counter.
@@ -858,6 +1018,26 @@ uint32_t Engine::fw_allreduce(EmuCall &c) {
     m.res = imm(x.a2, x.res_c());
     m.count = x.count;
     return execute(x, m);
+  }
+  {
+    const uint64_t bytes = static_cast<uint64_t>(x.count) * x.ubytes();
+    const bool oneshot = bytes <= (32u << 10) || x.count % P != 0; // plan.hpp: ll_oneshot_max / shards must split evenly
+    if (one_hop(x, oneshot ? bytes : bytes / P)) {
+      if (oneshot) return onehop_reduce(x, c.step, c.mask, x.a0, 0, x.a2, x.count);
+      // two hops: reduce-scatter into my shard of the result, then all-gather the shards (phase in bit 31 of the mask)
+      const uint32_t shard = x.count / P;
+      const uint64_t sb = static_cast<uint64_t>(shard) * x.ubytes();
+      if (!(c.mask & 0x80000000u)) {
+        uint32_t rc = onehop_reduce(x, c.step, c.mask, x.a0, sb, x.a2 + me * sb, shard);
+        if (rc) return rc;
+        c.step = 0;
+        c.mask = 0x80000000u;
+      }
+      uint32_t mask = c.mask & 0x7FFFFFFFu;
+      uint32_t rc = onehop_gather(x, c.step, mask, x.a2 + me * sb, x.a2, sb, shard);
+      c.mask = mask | 0x80000000u;
+      return rc;
+    }
   }
   if (!x.eager) {
     // rendezvous: reduce to rank 0, then broadcast from it

@@ -153,6 +153,12 @@ void ACCL::configure_tuning_parameters() {
   cclo->write(exchmem::BCAST_FLAT_TREE_MAX_RANKS, 3);
   cclo->write(exchmem::REDUCE_FLAT_TREE_MAX_RANKS, 4);
   cclo->write(exchmem::REDUCE_FLAT_TREE_MAX_COUNT, 32 * 1024);
+  cclo->write(exchmem::ONE_HOP_SCHEDULES, one_hop_schedules_ ? 1 : 0);
+}
+
+void ACCL::set_one_hop_schedules(bool on) {
+  one_hop_schedules_ = on;
+  cclo->write(exchmem::ONE_HOP_SCHEDULES, on ? 1 : 0);
 }
 
 void ACCL::configure_arithmetic() {

@@ -252,6 +252,39 @@ void suite(int W) {
         for (unsigned i = 0; i < n; ++i) CHECK(close((*d)[i], e[static_cast<unsigned>(r) * n + i], 1e-5f, 1e-4f));
       });
     }
+    // ---- the same collectives on the one-hop schedules of the B200 backend (ACCL::set_one_hop_schedules): one-shot and
+    // two-shot all-reduce (in place too), direct all-gather / reduce-scatter, fan-in reduce / gather
+    run_case("one_hop_schedules", W, *cfg, [](ACCL &a, int r, int w) {
+      a.set_one_hop_schedules(true);
+      const unsigned big = 4096u * static_cast<unsigned>(w); // splits evenly: reduce-scatter + all-gather
+      for (unsigned n : {24u, big, COUNT}) {                 // 24: everybody sends everything; COUNT: may not split
+        auto s = fbuf(a, n), d = fbuf(a, n);
+        fill(*s, data(n, r));
+        a.free_request(a.allreduce(*s, *d, n, reduceFunction::SUM));
+        auto e = reduced(w, n, reduceFunction::SUM);
+        for (unsigned i = 0; i < n; ++i) CHECK(close((*d)[i], e[i], 1e-5f, 1e-4f));
+        a.free_request(a.allreduce(*s, *s, n, reduceFunction::MAX)); // in place
+        auto m = reduced(w, n, reduceFunction::MAX);
+        for (unsigned i = 0; i < n; ++i) CHECK((*s)[i] == m[i]);
+      }
+      const unsigned n = 70;
+      auto s = fbuf(a, n * static_cast<unsigned>(w)), d = fbuf(a, n * static_cast<unsigned>(w)), o = fbuf(a, n);
+      fill(*s, data(n * static_cast<unsigned>(w), r));
+      a.free_request(a.reduce_scatter(*s, *o, n, reduceFunction::SUM));
+      auto e = reduced(w, n * static_cast<unsigned>(w), reduceFunction::SUM);
+      for (unsigned i = 0; i < n; ++i) CHECK(close((*o)[i], e[static_cast<unsigned>(r) * n + i], 1e-5f, 1e-4f));
+      a.free_request(a.allgather(*o, *d, n));
+      for (unsigned i = 0; i < n * static_cast<unsigned>(w); ++i) CHECK(close((*d)[i], e[i], 1e-5f, 1e-4f));
+      for (unsigned root = 0; root < static_cast<unsigned>(w); ++root) {
+        a.free_request(a.reduce(*s, *d, n, root, reduceFunction::SUM));
+        if (static_cast<unsigned>(r) == root)
+          for (unsigned i = 0; i < n; ++i) CHECK(close((*d)[i], e[i], 1e-5f, 1e-4f));
+        a.free_request(a.gather(*o, *d, n, root));
+        if (static_cast<unsigned>(r) == root)
+          for (unsigned i = 0; i < n * static_cast<unsigned>(w); ++i) CHECK(close((*d)[i], e[i], 1e-5f, 1e-4f));
+      }
+      a.set_one_hop_schedules(false);
+    });
     run_case("allreduce_compressed", W, *cfg, [](ACCL &a, int r, int w) {
       auto s = fbuf(a, COUNT), d = fbuf(a, COUNT);
       fill(*s, data(COUNT, r));
