@@ -97,10 +97,10 @@ step = st.tuples(st.sampled_from(OPS + ["barrier"]), st.integers(1, 3000), st.in
 
 
 @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow])
-@given(world=st.integers(2, 6), steps=st.lists(step, min_size=1, max_size=5), cfg=geometry())
-def test_collectives_match_reference(world, steps, cfg):
+@given(world=st.integers(2, 6), steps=st.lists(step, min_size=1, max_size=5), cfg=geometry(), one_hop=st.booleans())
+def test_collectives_match_reference(world, steps, cfg, one_hop):
     """A random program of 1-5 calls on one world: sequence numbers, rx-pool reuse and parked calls carry over
-    from one call to the next."""
+    from one call to the next.  `one_hop`: the reference-style rings / trees or the B200 backend's one-hop schedules."""
     always_eager = cfg["max_egr_size"] >= (1 << 20)
     if always_eager:
         # messages must fit the rx pool as a whole
@@ -108,6 +108,7 @@ def test_collectives_match_reference(world, steps, cfg):
 
     def fn(a, r, w):
         a.set_timeout(30_000_000)   # eager waits: peers may be seconds late on a loaded machine
+        a.set_one_hop_schedules(one_hop)
         for op, count, root, func, salt in steps:
             run_op(a, r, w, op, min(count, 2000) if always_eager else count, root % w, func, salt)
     A.run_ranks(world, fn, cfg, timeout=120.0)
@@ -186,8 +187,8 @@ def test_dtypes_and_wire_compression(op, world, count, root, func, dtype, wire, 
 
 @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
 @given(world=st.integers(3, 5), data_=st.data(), op=st.sampled_from(["allreduce", "bcast", "allgather", "reduce_scatter"]),
-       count=st.integers(1, 1200), func=st.sampled_from([SUM, MAX]), cfg=geometry(), salt=st.integers(0, 100))
-def test_subcommunicators(world, data_, op, count, func, cfg, salt):
+       count=st.integers(1, 1200), func=st.sampled_from([SUM, MAX]), cfg=geometry(), salt=st.integers(0, 100), one_hop=st.booleans())
+def test_subcommunicators(world, data_, op, count, func, cfg, salt, one_hop):
     """A random subset of the ranks forms a communicator and runs a collective while the others stay out; then
     everybody meets on the global communicator again (independent sequence spaces, reference test.cpp:701-832)."""
     members = sorted(data_.draw(st.sets(st.integers(0, world - 1), min_size=2, max_size=world)))
@@ -197,6 +198,7 @@ def test_subcommunicators(world, data_, op, count, func, cfg, salt):
         count = min(count, 1000)
 
     def fn(a, r, w):
+        a.set_one_hop_schedules(one_hop)
         a.set_timeout(30_000_000)
         if r in members:
             ranks = [a.get_comm_group(0)[m] for m in members]
@@ -256,6 +258,7 @@ def test_point_to_point_programs(world, cfg, salt, msgs):
 
     def fn(a, r, w):
         a.set_timeout(30_000_000)
+        a.set_one_hop_schedules(one_hop)
         pending, keep = [], []
         for i, (s, d, n, tag, any_) in enumerate(prog):
             if r == s:
@@ -277,8 +280,8 @@ def test_point_to_point_programs(world, cfg, salt, msgs):
 @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
 @given(world=st.integers(2, 4), cfg=geometry(), salt=st.integers(0, 1000),
        calls=st.lists(st.tuples(st.sampled_from(["allreduce", "bcast", "allgather"]), st.integers(1, 1500), st.integers(0, 3)),
-                      min_size=2, max_size=6))
-def test_async_collectives_in_flight(world, cfg, salt, calls):
+                      min_size=2, max_size=6), one_hop=st.booleans())
+def test_async_collectives_in_flight(world, cfg, salt, calls, one_hop):
     """Several collectives issued back to back with run_async=True, waited for afterwards: the engine keeps them all
     in flight; collectives on one communicator must still execute in issue order on every rank."""
     always_eager = cfg["max_egr_size"] >= (1 << 20)
@@ -287,6 +290,7 @@ def test_async_collectives_in_flight(world, cfg, salt, calls):
 
     def fn(a, r, w):
         a.set_timeout(30_000_000)
+        a.set_one_hop_schedules(one_hop)
         issued = []
         for i, (op, count, root) in enumerate(calls):
             count = min(count, 1000) if always_eager else count
@@ -323,8 +327,9 @@ mixed_step = st.one_of(
 
 
 @settings(max_examples=80, deadline=None, suppress_health_check=[HealthCheck.too_slow])
-@given(world=st.integers(2, 5), cfg=geometry(), salt=st.integers(0, 1000), steps=st.lists(mixed_step, min_size=2, max_size=8))
-def test_mixed_point_to_point_and_collectives(world, cfg, salt, steps):
+@given(world=st.integers(2, 5), cfg=geometry(), salt=st.integers(0, 1000), steps=st.lists(mixed_step, min_size=2, max_size=8),
+       one_hop=st.booleans())
+def test_mixed_point_to_point_and_collectives(world, cfg, salt, steps, one_hop):
     """Asynchronous (possibly parked) sends interleaved with blocking collectives: a rank sitting in a collective must
     still get its parked rendezvous sends out, or the peer that needs them never joins the collective."""
     always_eager = cfg["max_egr_size"] >= (1 << 20)
@@ -333,6 +338,7 @@ def test_mixed_point_to_point_and_collectives(world, cfg, salt, steps):
 
     def fn(a, r, w):
         a.set_timeout(30_000_000)
+        a.set_one_hop_schedules(one_hop)
         pending, keep = [], []
         for i, st_ in enumerate(steps):
             if st_[0] == "coll":
