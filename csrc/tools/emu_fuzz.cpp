@@ -160,6 +160,7 @@ int main(int argc, char **argv) {
     const unsigned buf = bufs[pick(0, 4)], nb = nbs[pick(0, 2)];
     unsigned egr = std::max(std::min(egrs[pick(0, 3)], buf * nb / 2), buf);
     const unsigned rv = std::max(rvs[pick(0, 3)], 2 * egr);
+    const bool one_hop = pick(0, 1) != 0; // reference-style rings / trees, or the one-hop schedules of the B200 backend
     std::vector<Step> steps(pick(1, 5));
     for (auto &s : steps) {
       s = Step{static_cast<Op>(pick(0, N_OPS - 1)), pick(1, 3000), pick(0, 5), pick(0, 1) ? reduceFunction::SUM : reduceFunction::MAX, pick(0, 1000)};
@@ -182,6 +183,7 @@ int main(int argc, char **argv) {
           accls[static_cast<size_t>(r)]->initialize(ranks, r, static_cast<int>(nb), buf, egr, rv);
           accls[static_cast<size_t>(r)]->free_request(accls[static_cast<size_t>(r)]->set_timeout(30000000)); // peers may be seconds late under a sanitizer
           ACCL &a = *accls[static_cast<size_t>(r)];
+          a.set_one_hop_schedules(one_hop);
           std::vector<ACCLRequest *> pending;
           std::vector<std::unique_ptr<Buffer<float>>> keep;
           for (const Step &s : steps) {
