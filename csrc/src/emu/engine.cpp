@@ -745,14 +745,16 @@ uint32_t Engine::execute(Ctx &x, const Move &m) {
   return err;
 }
 
-uint64_t one_hop_dispatches(); // firmware.cpp
+uint64_t one_hop_dispatches();              // firmware.cpp
+uint64_t one_hop_allreduce_forms(bool two_shot);
 
 std::string Engine::debug_state() {
   std::ostringstream o;
   std::lock_guard<std::mutex> g(q_m_);
   o << "emulator rank " << rank_ << ": new=" << new_calls_.size() << " parked=" << retry_calls_.size()
     << " addr_notes=" << addr_notes_.size() << " done_notes=" << done_notes_.size()
-    << " one_hop_dispatches=" << one_hop_dispatches();
+    << " one_hop_dispatches=" << one_hop_dispatches() << " allreduce_one_shot=" << one_hop_allreduce_forms(false)
+    << " allreduce_two_shot=" << one_hop_allreduce_forms(true);
   for (const auto &c : retry_calls_)
     o << "\n  parked: " << operation_name(static_cast<operation>(c.desc.scenario)) << " count=" << c.desc.count
       << " peer/root=" << c.desc.root_src_dst << " tag=" << c.desc.tag << " step=" << c.step << " mask=0x" << std::hex << c.mask

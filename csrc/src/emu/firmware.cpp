@@ -14,6 +14,7 @@
 #include <atomic>
 
 #include "accl/common.hpp"
+#include "accl/cuda/plan.hpp" // the B200 backend's call planner (host / device shared, plain C++): one-hop schedule selection
 #include "engine_ctx.hpp"
 
 namespace accl {
@@ -663,9 +664,11 @@ uint32_t Engine::fw_gather(EmuCall &c) {
 // data flow and the in-place hazards of the GPU schedules.  Uncompressed, non-stream calls only (as on the GPU, where
 // compressed / stream calls take other paths); everything else keeps the ring / tree forms.
 namespace {
-std::atomic<uint64_t> g_one_hop_dispatches{0}; // process-wide statistic (ranks as threads share it): shown by debug_state
+std::atomic<uint64_t> g_one_hop_dispatches{0}; // process-wide statistics (ranks as threads share them): shown by debug_state
+std::atomic<uint64_t> g_allreduce_one_shot{0}, g_allreduce_two_shot{0};
 }
 uint64_t one_hop_dispatches() { return g_one_hop_dispatches.load(); }
+uint64_t one_hop_allreduce_forms(bool two_shot) { return two_shot ? g_allreduce_two_shot.load() : g_allreduce_one_shot.load(); }
 
 bool Engine::one_hop(const Ctx &x, uint64_t landing_bytes) {
   if (!read_exch(exchmem::ONE_HOP_SCHEDULES) || x.cflags || x.sflags || x.comm.size < 2) return false;
@@ -1020,9 +1023,34 @@ uint32_t Engine::fw_allreduce(EmuCall &c) {
     return execute(x, m);
   }
   {
+    // one hop (everybody sends everything) or two (reduce-scatter + all-gather): what the CUDA backend's planner decides for
+    // this call — flag-in-data / slot-ring class: WF_ONESHOT rule; rendezvous class: one-shot while bytes * P <= 2 MiB
     const uint64_t bytes = static_cast<uint64_t>(x.count) * x.ubytes();
-    const bool oneshot = bytes <= (32u << 10) || x.count % P != 0; // plan.hpp: ll_oneshot_max / shards must split evenly
+    uint32_t ex[16] = {};
+    ex[exchmem::MAX_EAGER_SIZE / 4] = x.max_eager;
+    ex[exchmem::EAGER_RX_BUF_SIZE / 4] = x.rxbuf_size;
+    cuda::PlanCfg pc{};
+    pc.max_ctas = 128;
+    pc.nvls_min_ranks = 3;
+    pc.has_mc = 1;
+    pc.heap_world = P;
+    pc.oneshot_max_bytes = 2u << 20;
+    pc.nvls_ops = cuda::NVLS_OPS_DEFAULT;
+    pc.nvls_ctas = 32;
+    pc.ll_bytes = 2u << 20;
+    pc.ll_max_bytes = 2u << 20;
+    pc.ll_oneshot_max = 32u << 10;
+    cuda::WorkItem wi{};
+    wi.desc = c.desc;
+    wi.comm_size = P;
+    wi.udtype = static_cast<uint32_t>(x.ar.u);
+    wi.cdtype = static_cast<uint32_t>(x.ar.c);
+    cuda::plan_call(ex, pc, wi);
+    const bool planner_oneshot = wi.algo == cuda::ALGO_P2P_ONESHOT || wi.algo == cuda::ALGO_EAGER ||
+                                 ((wi.algo == cuda::ALGO_LL || wi.algo == cuda::ALGO_STAGED) && (wi.flags & cuda::WF_ONESHOT));
+    const bool oneshot = planner_oneshot || x.count % P != 0; // (the two-shot form here needs equal shards)
     if (one_hop(x, oneshot ? bytes : bytes / P)) {
+      if (c.step == 0 && c.mask == 0) (oneshot ? g_allreduce_one_shot : g_allreduce_two_shot).fetch_add(1);
       if (oneshot) return onehop_reduce(x, c.step, c.mask, x.a0, 0, x.a2, x.count);
       // two hops: reduce-scatter into my shard of the result, then all-gather the shards (phase in bit 31 of the mask)
       const uint32_t shard = x.count / P;

@@ -205,3 +205,34 @@ def test_the_one_hop_handlers_really_run(cfg):
         return n0, n1, n2, n3
     for n0, n1, n2, n3 in A.run_ranks(world, fn, cfg):
         assert n1 == n0 and n2 >= n1 + 2 * world and n3 == n2
+
+
+def _stat(a, name):
+    return int(A._C.emu_debug_state(a.impl).split(name + "=")[1].split()[0])
+
+
+@pytest.mark.skipif(not A._C.with_cuda, reason="the planner hook lives in the CUDA build")
+@pytest.mark.parametrize("cfg,max_eager", [(EAGER, 1 << 20), (RNDZV, 64)], ids=["eager", "rndzv"])
+def test_one_shot_or_two_shot_is_the_planners_decision(cfg, max_eager):
+    """For the same (count, world, eager threshold) the emulator takes the form `plan_call` picks for the GPU:
+    flag-in-data class: one hop up to 32 KiB; rendezvous class: one hop while bytes x P <= 2 MiB."""
+    world = 4
+    Op = A._C.Operation
+    for count in (256, 8192, 65536, 262144):
+        p = A._C.cuda_plan(Op.allreduce, count, A.DataType.float32, world, max_eager_bytes=max_eager, ll_kb=2048)
+        want_one_shot = p["algo"] in ("p2p_oneshot", "eager") or (p["algo"] in ("ll", "staged") and p["oneshot"])
+
+        def fn(a, r, w, count=count):
+            s, d = a.create_buffer(count), a.create_buffer(count)
+            s.host[:] = data(count, r)
+            a.barrier()
+            one0, two0 = _stat(a, "allreduce_one_shot"), _stat(a, "allreduce_two_shot")
+            a.barrier()
+            a.allreduce(s, d, count, SUM)
+            a.barrier()
+            one1, two1 = _stat(a, "allreduce_one_shot"), _stat(a, "allreduce_two_shot")
+            a.barrier()
+            assert torch.equal(d.host, torch.stack([data(count, q) for q in range(w)]).sum(0))
+            return one1 - one0, two1 - two0
+        for one, two in run(world, fn, dict(cfg, max_rndzv_size=1 << 22)):
+            assert (one >= world and two == 0) if want_one_shot else (two >= world and one == 0), (count, p, one, two)
