@@ -258,7 +258,6 @@ def test_point_to_point_programs(world, cfg, salt, msgs):
 
     def fn(a, r, w):
         a.set_timeout(30_000_000)
-        a.set_one_hop_schedules(one_hop)
         pending, keep = [], []
         for i, (s, d, n, tag, any_) in enumerate(prog):
             if r == s:
