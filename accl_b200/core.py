@@ -386,7 +386,7 @@ class Accl:
 
     def cuda_debug_state(self):
         """CUDA backend: sync-pad / eager counters of this rank's control block (and the per-call phase
-        timing when built with ACCL_PHASE_TIMING).  Safe to call from another thread while a call hangs."""
+       .  Safe to call from another thread while a call hangs."""
         return _C.cuda_debug_state(self._a)
 
     def dump_eager_rx_buffers(self, dump_data=False):

@@ -72,7 +72,7 @@ def _compile(src, with_cuda, hdr_mtime, verbose, force):
         return obj
     defs = ["-DACCL_WITH_CUDA"] if with_cuda else []
     # extra -D switches for experiments, e.g.
-    # ACCL_EXTRA_DEFINES=ACCL_EXPERIMENTAL_REDUCE_PUSH python -m accl_b200.utils.build -f
+    # ACCL_EXTRA_DEFINES=MY_SWITCH python -m accl_b200.utils.build -f
     defs += ["-D" + d for d in os.environ.get("ACCL_EXTRA_DEFINES", "").split(",") if d]
     if src.endswith(".cu"):
         cmd = [NVCC, "-ccbin", CXX, "-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-fvisibility=hidden",
@@ -137,7 +137,7 @@ def build(with_cuda=True, verbose=False, force=False, tools=True, out_path=None)
 
 def check_experimental(defines, verbose=True):
     """Compile (do not link) every CUDA-backend source with extra -D switches into build/obj_exp: the way to
-    syntax- and resource-check code that is kept out of the default build (e.g. ACCL_EXPERIMENTAL_REDUCE_PUSH)."""
+    syntax- and resource-check code that is kept out of the default build (any -D switch)."""
     out = ROOT / "build" / "obj_exp"
     out.mkdir(parents=True, exist_ok=True)
     srcs = sorted(str(p.relative_to(CSRC)) for p in (CSRC / "src" / "cuda").glob("*.cu")) + \
@@ -166,7 +166,7 @@ def build_variant(name, defines, verbose=False):
     """A second, self-contained copy of the package built with extra -D switches:
     build/variants/<name>/accl_b200 (python sources copied, own _C extension, own object directory).
     `PYTHONPATH=build/variants/<name> python ...` then runs that build next to the default one — one GPU
-    session can compare both (e.g. ACCL_PHASE_TIMING, ACCL_EXPERIMENTAL_REDUCE_PUSH)."""
+    session can compare both (any set of -D switches)."""
     import shutil
     global OBJ
     pkg = ROOT / "build" / "variants" / name / "accl_b200"
