@@ -385,8 +385,8 @@ class Accl:
         _C.cuda_drain(self._a)
 
     def cuda_debug_state(self):
-        """CUDA backend: sync-pad / eager counters of this rank's control block (and the per-call phase
-       .  Safe to call from another thread while a call hangs."""
+        """CUDA backend: sync-pad / eager counters of this rank's control block.
+        Safe to call from another thread while a call hangs."""
         return _C.cuda_debug_state(self._a)
 
     def dump_eager_rx_buffers(self, dump_data=False):
