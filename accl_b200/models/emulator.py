@@ -123,6 +123,13 @@ def selftest():
         ref = sum(torch.arange(n, dtype=torch.float32) + q for q in range(w))
         assert torch.allclose(d.host, ref), "allreduce mismatch"
     a.barrier()
+    a.set_one_hop_schedules(True)   # the same all-reduces on the B200 backend's one-hop schedules
+    for n in (300, 20000):
+        s, d = a.create_buffer(n), a.create_buffer(n)
+        s.host[:] = torch.arange(n, dtype=torch.float32) + r
+        a.allreduce(s, d, n, A.SUM)
+        assert torch.allclose(d.host, sum(torch.arange(n, dtype=torch.float32) + q for q in range(w))), "one-hop allreduce mismatch"
+    a.barrier()
     a.deinit()
     print(f"emulator rank {r}/{w}: ok", flush=True)
 

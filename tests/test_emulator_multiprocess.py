@@ -51,6 +51,18 @@ def test_standalone_engine_processes_with_remote_drivers():
                 assert req.duration_ns() > 0
                 ref = sum(torch.arange(n, dtype=torch.float32) + q for q in range(world))
                 assert torch.allclose(d.host, ref)
+            # the one-hop schedules of the B200 backend inside a stand-alone engine: the register travels over the control socket
+            a.barrier()
+            a.set_one_hop_schedules(True)
+            for n in (300, 6000):   # rendezvous class, one hop: the whole vector lands in a scratch buffer (<= max_rndzv_size)
+                s, d = a.create_buffer(n), a.create_buffer(n)
+                s.host[:] = torch.arange(n, dtype=torch.float32) + r
+                a.allreduce(s, d, n, A.SUM)
+                assert torch.equal(d.host, sum(torch.arange(n, dtype=torch.float32) + q for q in range(world)))
+            assert "one_hop_dispatches=" in A._C.emu_remote_debug_state(a.impl)
+            assert int(A._C.emu_remote_debug_state(a.impl).split("one_hop_dispatches=")[1].split()[0]) >= 2
+            a.barrier()
+            a.set_one_hop_schedules(False)
             # stream port through the control connection (kernel loopback is on by default)
             s, d = a.create_buffer(64), a.create_buffer(64)
             s.host[:] = torch.arange(64, dtype=torch.float32) * (r + 1)
