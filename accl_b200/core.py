@@ -174,7 +174,10 @@ class Accl:
         allocated from `heap_mem_pool()`)."""
         if not (self.is_cuda and isinstance(t, torch.Tensor) and t.is_cuda and t.numel()):
             return False
-        base, size = _C.cuda_heap_range(self._a)
+        rng = getattr(self, "_heap_range", None)
+        if rng is None:
+            rng = self._heap_range = _C.cuda_heap_range(self._a)   # fixed for the life of the backend
+        base, size = rng
         p = t.data_ptr()
         return base <= p and p + t.numel() * t.element_size() <= base + size
 
