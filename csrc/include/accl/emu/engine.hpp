@@ -181,8 +181,11 @@ private:
   bool decode(EmuCall &c, Ctx &x, uint32_t &err);
   // one-hop schedules (exchmem::ONE_HOP_SCHEDULES): what the B200 backend's planner picks on an NVSwitch domain
   bool one_hop(const Ctx &x, uint64_t landing_bytes);
-  uint32_t onehop_gather(Ctx &x, uint32_t &step, uint32_t &mask, uint64_t own_block, uint64_t dst_base, uint64_t blk_bytes, uint32_t count);
-  uint32_t onehop_reduce(Ctx &x, uint32_t &step, uint32_t &mask, uint64_t src_base, uint64_t src_stride, uint64_t dst, uint32_t count);
+  // `last_extra`: elements the last rank's block has on top of `count` (two-shot all-reduce of a count that does not split)
+  uint32_t onehop_gather(Ctx &x, uint32_t &step, uint32_t &mask, uint64_t own_block, uint64_t dst_base, uint64_t blk_bytes, uint32_t count,
+                         uint32_t last_extra = 0);
+  uint32_t onehop_reduce(Ctx &x, uint32_t &step, uint32_t &mask, uint64_t src_base, uint64_t src_stride, uint64_t dst, uint32_t count,
+                         uint32_t last_extra = 0);
   void purge_notes_of(EmuCall &c);
 
   // eager building blocks (blocking, like the DMP)

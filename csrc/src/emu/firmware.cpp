@@ -680,21 +680,22 @@ bool Engine::one_hop(const Ctx &x, uint64_t landing_bytes) {
 // Every rank delivers `count` elements at own_block to slot `me` of every peer's dst_base (slots of blk_bytes).
 // step / mask: resumable state of a parked call (mask bits 0-15: peers written, bits 16-20: completions collected).
 uint32_t Engine::onehop_gather(Ctx &x, uint32_t &step, uint32_t &mask, uint64_t own_block, uint64_t dst_base, uint64_t blk_bytes,
-                               uint32_t count) {
+                               uint32_t count, uint32_t last_extra) {
   const uint32_t P = x.comm.size, me = x.comm.local_rank;
+  auto count_of = [&](uint32_t q) { return count + (q == P - 1 ? last_extra : 0); };
   uint32_t err = 0;
   if (x.eager) {
-    for (uint32_t k = 1; k < P && !err; ++k) err |= egr_send(x, (me + k) % P, imm(own_block), count, x.tag, false, 0);
+    for (uint32_t k = 1; k < P && !err; ++k) err |= egr_send(x, (me + k) % P, imm(own_block), count_of(me), x.tag, false, 0);
     for (uint32_t k = 1; k < P && !err; ++k) {
       const uint32_t from = (me + P - k) % P;
-      err |= egr_recv(x, from, imm(dst_base + from * blk_bytes), count, x.tag, false, 0);
+      err |= egr_recv(x, from, imm(dst_base + from * blk_bytes), count_of(from), x.tag, false, 0);
     }
     return err;
   }
   Steps st(step);
   st([&] {
     for (uint32_t r = 0; r < P; ++r)
-      if (r != me) rndzv_post_addr(x, r, dst_base + r * blk_bytes, count * x.ubytes(), x.tag);
+      if (r != me) rndzv_post_addr(x, r, dst_base + r * blk_bytes, count_of(r) * x.ubytes(), x.tag);
     return true;
   });
   const uint32_t all = ((1u << P) - 1) & ~(1u << me);
@@ -702,7 +703,7 @@ uint32_t Engine::onehop_gather(Ctx &x, uint32_t &step, uint32_t &mask, uint64_t 
     uint32_t to = 0;
     uint64_t vaddr = 0;
     if (!rndzv_take_any_addr(x, (mask & 0xFFFFu) | (1u << me), x.tag, to, vaddr)) return NOT_READY_ERROR;
-    err = rndzv_write(x, to, own_block, vaddr, count, x.tag);
+    err = rndzv_write(x, to, own_block, vaddr, count_of(me), x.tag);
     if (err) return err;
     mask |= 1u << to;
   }
@@ -719,17 +720,19 @@ uint32_t Engine::onehop_gather(Ctx &x, uint32_t &step, uint32_t &mask, uint64_t 
 // Rendezvous form: contributions land one at a time in scratch 0 and are folded ping-pong through scratch 1 / 2; the
 // fold that writes dst waits until this rank has delivered all of its own contributions (dst may alias the source).
 uint32_t Engine::onehop_reduce(Ctx &x, uint32_t &step, uint32_t &mask, uint64_t src_base, uint64_t src_stride, uint64_t dst,
-                               uint32_t count) {
+                               uint32_t count, uint32_t last_extra) {
   const uint32_t P = x.comm.size, me = x.comm.local_rank;
+  auto count_of = [&](uint32_t q) { return count + (q == P - 1 ? last_extra : 0); };
+  const uint32_t mine = count_of(me);
   uint32_t err = 0;
   if (x.eager) {
     for (uint32_t k = 1; k < P && !err; ++k) {
       const uint32_t to = (me + k) % P;
-      err |= egr_send(x, to, imm(src_base + to * src_stride), count, x.tag, false, 0);
+      err |= egr_send(x, to, imm(src_base + to * src_stride), count_of(to), x.tag, false, 0);
     }
     Operand acc = imm(src_base + me * src_stride);
     for (uint32_t k = 1; k < P && !err; ++k) {
-      err |= egr_recv_reduce(x, (me + P - k) % P, acc, imm(dst), count, x.tag);
+      err |= egr_recv_reduce(x, (me + P - k) % P, acc, imm(dst), mine, x.tag);
       acc = imm(dst);
     }
     return err;
@@ -742,7 +745,7 @@ uint32_t Engine::onehop_reduce(Ctx &x, uint32_t &step, uint32_t &mask, uint64_t 
       uint32_t to = 0;
       uint64_t vaddr = 0;
       if (!rndzv_take_any_addr(x, (mask & 0xFFFFu) | (1u << me), x.tag, to, vaddr)) break;
-      err = rndzv_write(x, to, src_base + to * src_stride, vaddr, count, x.tag);
+      err = rndzv_write(x, to, src_base + to * src_stride, vaddr, count_of(to), x.tag);
       if (err) return err;
       mask |= 1u << to;
       progressed = true;
@@ -751,7 +754,7 @@ uint32_t Engine::onehop_reduce(Ctx &x, uint32_t &step, uint32_t &mask, uint64_t 
     if (served < P - 1) { // owner role
       const uint32_t from = (me + P - 1 - served) % P;
       if (!(step & 1u)) {
-        rndzv_post_addr(x, from, x.spare[0], count * x.ubytes(), x.tag);
+        rndzv_post_addr(x, from, x.spare[0], mine * x.ubytes(), x.tag);
         step |= 1u;
         progressed = true;
       }
@@ -761,7 +764,7 @@ uint32_t Engine::onehop_reduce(Ctx &x, uint32_t &step, uint32_t &mask, uint64_t 
         m.op0 = imm(served == 0 ? src_base + me * src_stride : x.spare[1 + (served & 1)]);
         m.op1 = imm(x.spare[0]);
         m.res = imm(last ? dst : x.spare[1 + ((served + 1) & 1)]);
-        m.count = count;
+        m.count = mine;
         m.func = x.fn();
         err = execute(x, m);
         if (err) return err;
@@ -1048,21 +1051,22 @@ uint32_t Engine::fw_allreduce(EmuCall &c) {
     cuda::plan_call(ex, pc, wi);
     const bool planner_oneshot = wi.algo == cuda::ALGO_P2P_ONESHOT || wi.algo == cuda::ALGO_EAGER ||
                                  ((wi.algo == cuda::ALGO_LL || wi.algo == cuda::ALGO_STAGED) && (wi.flags & cuda::WF_ONESHOT));
-    const bool oneshot = planner_oneshot || x.count % P != 0; // (the two-shot form here needs equal shards)
-    if (one_hop(x, oneshot ? bytes : bytes / P)) {
+    // two hops with a count that does not split: the last rank's shard absorbs the remainder (as on the GPU)
+    const uint32_t shard = x.count / P, extra = x.count % P;
+    const bool oneshot = planner_oneshot || shard == 0;
+    if (one_hop(x, oneshot ? bytes : static_cast<uint64_t>(shard + extra) * x.ubytes())) {
       if (c.step == 0 && c.mask == 0) (oneshot ? g_allreduce_one_shot : g_allreduce_two_shot).fetch_add(1);
       if (oneshot) return onehop_reduce(x, c.step, c.mask, x.a0, 0, x.a2, x.count);
-      // two hops: reduce-scatter into my shard of the result, then all-gather the shards (phase in bit 31 of the mask)
-      const uint32_t shard = x.count / P;
+      // reduce-scatter into my shard of the result, then all-gather the shards (phase in bit 31 of the mask)
       const uint64_t sb = static_cast<uint64_t>(shard) * x.ubytes();
       if (!(c.mask & 0x80000000u)) {
-        uint32_t rc = onehop_reduce(x, c.step, c.mask, x.a0, sb, x.a2 + me * sb, shard);
+        uint32_t rc = onehop_reduce(x, c.step, c.mask, x.a0, sb, x.a2 + me * sb, shard, extra);
         if (rc) return rc;
         c.step = 0;
         c.mask = 0x80000000u;
       }
       uint32_t mask = c.mask & 0x7FFFFFFFu;
-      uint32_t rc = onehop_gather(x, c.step, mask, x.a2 + me * sb, x.a2, sb, shard);
+      uint32_t rc = onehop_gather(x, c.step, mask, x.a2 + me * sb, x.a2, sb, shard, extra);
       c.mask = mask | 0x80000000u;
       return rc;
     }

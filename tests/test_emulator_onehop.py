@@ -34,8 +34,9 @@ def run(world, fn, cfg):
 @pytest.mark.parametrize("world", WORLDS)
 @pytest.mark.parametrize("func", [SUM, MAX])
 def test_allreduce_one_shot_two_shot_and_odd_counts(world, cfg, func):
-    # 24: one-shot (small); 8192 * world elements: two-shot (shards split evenly); 9001: does not split -> one-shot
-    for count in (24, 8192 * world, 9001):
+    # 24: one hop (small); 8192 * world elements: two hops, shards split evenly; 9001: does not split (flag-in-data class: one hop);
+    # 200003: rendezvous class, bytes x P > 2 MiB and a remainder: two hops, the last rank's shard absorbs the remainder
+    for count in (24, 8192 * world, 9001, 200003):
         def fn(a, r, w, count=count):
             s, d = a.create_buffer(count), a.create_buffer(count)
             s.host[:] = data(count, r)
