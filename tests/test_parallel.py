@@ -1,5 +1,6 @@
 """Torch-facing layer on the CPU emulator: TensorGroup, GradBucket, ring_exchange and the registered
 `torch.ops.accl_b200.*` custom ops (same code paths the CUDA backend uses, minus stream ordering)."""
+import pytest
 import torch
 
 import accl_b200 as A
@@ -97,13 +98,15 @@ def test_registered_torch_ops():
     A.run_ranks(W, fn, CFG)
 
 
-def test_zero_optimizer_matches_plain_sgd():
+@pytest.mark.parametrize("one_hop", [False, True], ids=["rings", "one_hop"])
+def test_zero_optimizer_matches_plain_sgd(one_hop):
     from accl_b200.parallel.strategies import ZeroOptimizer
     torch.manual_seed(0)
     w0, b0 = torch.randn(4, 5), torch.randn(7)
     grads = [[torch.randn(4, 5, generator=torch.Generator().manual_seed(10 * s + r)) for r in range(W)] for s in range(3)]
 
     def fn(a, r, w):
+        a.set_one_hop_schedules(one_hop)   # reference-style rings / trees, or the B200 backend's schedules
         g = TensorGroup(a)
         pw, pb = w0.clone(), b0.clone()
         opt = ZeroOptimizer(g, [pw, pb], lr=0.5, momentum=0.9)
@@ -124,13 +127,15 @@ def test_zero_optimizer_matches_plain_sgd():
         assert torch.allclose(w_, pw, atol=1e-5) and torch.allclose(b_, pb, atol=1e-5)
 
 
-def test_column_parallel_pipeline_moe_ulysses():
+@pytest.mark.parametrize("one_hop", [False, True], ids=["rings", "one_hop"])
+def test_column_parallel_pipeline_moe_ulysses(one_hop):
     from accl_b200.parallel.strategies import (ColumnParallelLinear, moe_combine, moe_dispatch, pipeline_recv,
                                                pipeline_send, ulysses_head_to_seq, ulysses_seq_to_head)
     S, H, D = 6 * W, 2 * W, 4
     full = torch.arange(S * H * D, dtype=torch.float32).view(S, H, D)
 
     def fn(a, r, w):
+        a.set_one_hop_schedules(one_hop)
         g = TensorGroup(a)
         # column-parallel linear with gathered output == the unsharded GEMM
         lin = ColumnParallelLinear(g, 8, 3, gather_output=True)
