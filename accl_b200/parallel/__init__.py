@@ -53,6 +53,8 @@ def init_from_env(backend=None, **kw):
     else:
         acc = socket_rank(**kw)
     acc.initialize(**init_kw)
+    if backend != "cuda" and os.environ.get("ACCL_EMU_ONE_HOP", "0") not in ("", "0"):
+        acc.set_one_hop_schedules(True)   # emulator: the B200 backend's schedules instead of the reference's rings / trees
     return acc
 
 

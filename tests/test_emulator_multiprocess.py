@@ -136,12 +136,13 @@ def test_cpp_example_links_against_the_static_library(tmp_path):
     assert r.returncode == 0 and "all ranks ok" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("one_hop", ["0", "1"], ids=["rings", "one_hop"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_torch_distributed_backend(world):
+def test_torch_distributed_backend(world, one_hop):
     """`dist.init_process_group("accl")`: all_reduce / broadcast / all_gather / reduce_scatter / all_to_all /
     reduce / send / recv / barrier and DistributedDataParallel through the standard torch.distributed API."""
     import random
-    env = dict(os.environ, PG_PORT=str(random.randint(20000, 40000)))
+    env = dict(os.environ, PG_PORT=str(random.randint(20000, 40000)), ACCL_EMU_ONE_HOP=one_hop)
     r = subprocess.run([sys.executable, "-m", "accl_b200.models.emulator", "-n", str(world), "--", sys.executable,
                         os.path.join(ROOT, "tests", "helpers", "pg_worker.py")], cwd=ROOT, env=env, capture_output=True,
                        text=True, timeout=300)
