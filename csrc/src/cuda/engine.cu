@@ -602,7 +602,10 @@ __device__ void engine_control(const DevWorld &w, HostRing *hr, int nworkers) {
         if (stop || (idle_long && s_nactive == 0 && hr->pins == 0 && hr->clients == dev::ld_acquire_sys(&me->clients_done))) {
           hr->state = ENG_EXITING;
           dev::fence_sc_sys();
-          const bool pending = hr->submitted != s_host_fetched || dev::ld_acquire_sys(&me->cmd_ready[fetched % RING_SLOTS]) == fetched + 1;
+          // Dekker handshake with the host (submit / pin / client_begin write their word, fence, then read `state`): everything
+          // that may have changed since the decision above is read again AFTER `state = EXITING` has been published
+          const bool pending = hr->submitted != s_host_fetched || dev::ld_acquire_sys(&me->cmd_ready[fetched % RING_SLOTS]) == fetched + 1 ||
+                               hr->pins != 0 || hr->clients != dev::ld_acquire_sys(&me->clients_done);
           if ((pending || s_nactive != 0) && !stop) hr->state = ENG_RUNNING; // a submit raced with parking: keep going
           else leave = 1;
         }
