@@ -96,3 +96,51 @@ def test_channel_counts():
     assert plan(Op.allreduce, 256 << 20, max_ctas=1000, nvls_min_ranks=99)["n_ctas"] <= 128   # never more channels than sync pads
     assert plan(Op.copy, 1 << 30)["algo"] == "local" and plan(Op.copy, 1 << 30)["n_ctas"] == 296
     assert plan(Op.barrier, 0)["n_ctas"] == 1 and plan(Op.nop, 0)["algo"] == "local"
+
+
+# ---- invariants over random calls and configurations (the planner runs on every rank and on the device: whatever it
+# returns must be executable by the protocol it names)
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+COLLECTIVES = [Op.allreduce, Op.allgather, Op.reduce_scatter, Op.bcast, Op.scatter, Op.gather, Op.reduce, Op.alltoall]
+
+
+@settings(max_examples=600, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(op=st.sampled_from(COLLECTIVES + [Op.send, Op.recv]), count=st.integers(1, 1 << 28), world=st.integers(2, 8),
+       max_eager=st.sampled_from([1024, 64 << 10, 1 << 20, 4 << 20]), max_ctas=st.sampled_from([1, 8, 32, 64, 128, 1000]),
+       has_mc=st.booleans(), ll_kb=st.sampled_from([0, 64, 256, 2048]), stage_kb=st.sampled_from([0, 1024]),
+       staged_max=st.sampled_from([0, 1 << 20]), engine_mode=st.booleans(), compressed=st.booleans())
+def test_plans_are_executable(op, count, world, max_eager, max_ctas, has_mc, ll_kb, stage_kb, staged_max, engine_mode, compressed):
+    p = A._C.cuda_plan(op, count, F32, world, max_eager_bytes=max_eager, max_ctas=max_ctas, has_mc=has_mc, ll_kb=ll_kb,
+                       stage_kb=stage_kb, staged_max_bytes=staged_max, engine_mode=engine_mode, compressed=compressed)
+    nbytes = count * 4
+    assert p["algo"] in ("eager", "nvls", "p2p", "p2p_oneshot", "ll", "staged", "wire")
+    assert 1 <= p["n_ctas"] <= min(max(max_ctas, 1), 128)                     # never more channels than sync pads / the cap
+    if p["algo"] in ("ll", "staged"):
+        assert nbytes <= max_eager and not compressed and op not in (Op.send, Op.recv)
+        assert p["n_ctas"] <= 32                                              # staging regions are cut into 32 channel slices
+        m = nbytes // world if (op == Op.allreduce and not p["oneshot"]) else nbytes
+        region = (ll_kb if p["algo"] == "ll" else stage_kb) << 10
+        assert 0 < m <= region // (2 if p["algo"] == "ll" else 1)             # the message fits its staging region
+        if p["algo"] == "ll":
+            assert m * (world - 1) <= 2 << 20                                 # the fan-out budget
+    if p["oneshot"]:
+        assert op == Op.allreduce and p["algo"] in ("ll", "staged")
+    if p["algo"] == "nvls":
+        assert has_mc and world >= 3 and op in (Op.allreduce, Op.bcast, Op.reduce)
+    if p["algo"] == "p2p_oneshot":
+        assert op == Op.allreduce and nbytes * world <= 2 << 20
+    if op in (Op.send, Op.recv):
+        assert p["algo"] in ("eager", "p2p") and (p["algo"] == "p2p" or p["n_ctas"] == 1)
+    if nbytes > max_eager and not compressed:
+        assert p["algo"] in ("nvls", "p2p", "p2p_oneshot")                    # rendezvous class
+
+
+@settings(max_examples=200, deadline=None)
+@given(op=st.sampled_from(COLLECTIVES), world=st.integers(2, 8), lo=st.integers(1, 1 << 20))
+def test_channel_count_grows_with_the_message_within_one_protocol(op, world, lo):
+    """Within one algorithm a larger message never gets fewer channels."""
+    a = plan(op, lo * 4, world=world, max_eager_bytes=4 << 20, ll_kb=2048)
+    b = plan(op, lo * 8, world=world, max_eager_bytes=4 << 20, ll_kb=2048)
+    if a["algo"] == b["algo"] and a["oneshot"] == b["oneshot"]:
+        assert b["n_ctas"] >= a["n_ctas"], (a, b)
